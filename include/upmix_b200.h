@@ -1,0 +1,130 @@
+/* upmix_b200.h -- C ABI of the B200-native multi-band STFT centre-extraction path.
+ *
+ * This is the drop-in boundary for the hot path of willleskowitz/upmix.  Plain pointers and sizes,
+ * no C++ or torch types, no exceptions: every call returns 0 on success or a negative UPMIX_E_* code,
+ * and upmix_last_error() gives the message for the calling thread.  All device memory is owned by the
+ * caller (signal, outputs, workspace, streaming state); a plan owns only its read-only tables.  A plan
+ * is immutable after creation, belongs to one device, and may be used from one stream at a time.
+ *
+ * Reference interfaces each entry point replaces (paths under the reference repository):
+ *   python-prototype/center_extraction.py   (CE)      bela/upmix.cpp   (BU)
+ *
+ *   upmix_plan_create        <- the per-band state built by MultiBandExtractorAccu.__init__ (CE:240-271)
+ *                               for every band of chain_bands (CE:518-580); C++ twin
+ *                               Overlap75UpmixBand::setup / MultiBandUpmix::setup (BU:176-226, 439-471)
+ *   upmix_process            <- extract_center_left_right_multi_band_in_memory (CE:477-513), i.e.
+ *                               process_all_blocks of every band (CE:426-472) + the band sum (CE:503-511)
+ *   upmix_process_segment    <- same, for one time shard of a track (no reference equivalent: the
+ *                               reference keeps the whole signal in memory, CE:444-445)
+ *   upmix_stream_block       <- process_stereo_chunk / flush_final state carried between calls
+ *                               (CE:353-424) and MultiBandUpmix::process (BU:474-493)
+ *   upmix_process_host       <- the same call as main.py makes (MP:78-80), with host buffers
+ */
+#ifndef UPMIX_B200_H
+#define UPMIX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct UpmixPlan UpmixPlan;
+
+/* One band, described by host tables (copied at plan creation).
+ * n_fft: STFT size, a power of two in [64, 65536].  hop: n_fft/4 (75 % overlap) -- any hop that
+ * divides n_fft is accepted for n_fft <= 8192; sizes above 8192 require hop == n_fft/4.
+ * ana / syn: analysis and synthesis windows, n_fft floats (CE:257-258).
+ * gain: per-bin real band-limit gain, n_fft/2+1 floats -- what _band_limit (CE:334-351) multiplies
+ * both spectra with. */
+typedef struct UpmixBandDesc {
+    int32_t n_fft;
+    int32_t hop;
+    const float* ana;
+    const float* syn;
+    const float* gain;
+} UpmixBandDesc;
+
+enum {
+    UPMIX_OUT_LSCRS = 0, /* three outputs: centre, left-side, right-side (CE:513 order: C, Ls, Rs) */
+    UPMIX_OUT_FOLD = 1   /* two outputs: Ls + 0.5 C, Rs + 0.5 C (BU:295-303; main.py "stereo_sum") */
+};
+
+enum {
+    UPMIX_OK = 0,
+    UPMIX_E_INVALID = -1,   /* bad argument */
+    UPMIX_E_UNSUPPORTED = -2, /* size / hop outside what the kernels implement */
+    UPMIX_E_CUDA = -3,      /* CUDA runtime error (message has the detail) */
+    UPMIX_E_WORKSPACE = -4  /* workspace too small */
+};
+
+/* Message of the last failing call on this thread (never NULL). */
+const char* upmix_last_error(void);
+
+/* ABI version: major*1000 + minor. */
+int upmix_version(void);
+
+int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int device, UpmixPlan** out);
+int upmix_plan_destroy(UpmixPlan* plan);
+int upmix_plan_n_bands(const UpmixPlan* plan);
+
+/* Bytes of device workspace upmix_process / upmix_process_segment need for seg_len output samples
+ * per track and n_tracks tracks (negative on error).  Any 256-byte-aligned device buffer will do. */
+int64_t upmix_workspace_bytes(const UpmixPlan* plan, int64_t seg_len, int n_tracks);
+
+/* Whole tracks.  L, R: device, planar float32, track t at L + t*in_stride, n_samples each.
+ * out_c / out_l / out_r: device float32, track t at out + t*out_stride.  In FOLD mode out_c may be NULL.
+ * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream). */
+int upmix_process(const UpmixPlan* plan, const float* L, const float* R, int64_t n_samples, int n_tracks,
+                  int64_t in_stride, float* out_c, float* out_l, float* out_r, int64_t out_stride,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* One time shard.  The track has n_total samples; L/R hold its samples [in_begin, in_begin+in_len)
+ * (index 0 = sample in_begin); outputs receive samples [seg_begin, seg_end) (index 0 = seg_begin).
+ * The input range must cover [seg_begin - (n_fft-hop), seg_end + (n_fft-hop)) clipped to the track
+ * for the plan's largest band; frames keep their global index, so the result is bit-identical to
+ * the same samples of an unsharded run. */
+int upmix_process_segment(const UpmixPlan* plan, const float* L, const float* R, int64_t in_begin, int64_t in_len,
+                          int64_t n_total, int64_t seg_begin, int64_t seg_end, int n_tracks, int64_t in_stride,
+                          float* out_c, float* out_l, float* out_r, int64_t out_stride, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
+/* Input margin (samples each side) upmix_process_segment needs: max over bands of n_fft - hop. */
+int64_t upmix_segment_halo(const UpmixPlan* plan);
+
+/* Block streaming (bands with n_fft <= 8192).  `state` is caller-owned device memory of
+ * upmix_stream_state_bytes(plan, n_tracks) bytes; upmix_stream_reset clears it.  Each call consumes
+ * n_new fresh samples per track (a multiple of every band's hop) and returns n_new output samples
+ * delayed by the plan's largest (n_fft - hop): out[i] of call j is sample j*n_new + i - delay of the
+ * offline result (zeros before the signal starts).  With hop-aligned blocks of hw samples and
+ * n_fft <= 4*hw this is the 3*hw latency of the Bela program (BU:232-237). */
+int64_t upmix_stream_state_bytes(const UpmixPlan* plan, int n_tracks);
+int64_t upmix_stream_workspace_bytes(const UpmixPlan* plan, int n_new, int n_tracks);
+int64_t upmix_stream_delay(const UpmixPlan* plan);
+int upmix_stream_reset(const UpmixPlan* plan, void* state, int n_tracks, void* stream);
+/* samples_done: samples per track consumed by the previous calls since the last reset (the caller
+ * keeps this count; the state itself is plain device memory). */
+int upmix_stream_block(const UpmixPlan* plan, void* state, int64_t samples_done, const float* in_l, const float* in_r,
+                       int n_new, int n_tracks, int64_t in_stride, float* out_c, float* out_l, float* out_r,
+                       int64_t out_stride, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* One frame of a single-band plan (n_fft <= 8192), the stateful API of the prototype
+ * (process_stereo_chunk, CE:353-409): blk_l / blk_r hold the n_fft samples of frame `frame_index`
+ * (device), `ring` is the caller-owned overlap-add state [track][3][n_fft] floats (zero it to start;
+ * its contents are the prototype's accumC/accumL/accumR, which is also what flush_final returns,
+ * CE:411-424), out_* receive the hop samples the frame finishes.  frame_index must increase by one
+ * per call.  Workspace: upmix_workspace_bytes(plan, hop, n_tracks). */
+int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, const float* blk_l, const float* blk_r,
+                     int n_tracks, int64_t in_stride, float* out_c, float* out_l, float* out_r, int64_t out_stride,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Host-buffer convenience: copies L/R (host float32) to the device, runs upmix_process, copies the
+ * outputs back, synchronises.  Allocates and frees its own device memory; for repeated calls use the
+ * device-pointer entry points. */
+int upmix_process_host(const UpmixPlan* plan, const float* L, const float* R, int64_t n_samples, float* out_c,
+                       float* out_l, float* out_r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UPMIX_B200_H */

@@ -1,0 +1,255 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the reference-facing
+surface (upmix_b200.center_extraction / bela) and hence through the C ABI; results are compared with
+the golden fixtures made from the unmodified reference and with the oracle on seeded inputs.
+
+Bar (BASELINE.json north_star): >= 100 dB SNR per output channel, max abs error <= 1e-5 of full scale.
+"""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from oracle import upmix_oracle as uo
+from tests.parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+@pytest.fixture(scope="module")
+def ce():
+    import torch
+    assert torch.cuda.is_available()
+    import upmix_b200.center_extraction as mod
+    from upmix_b200 import _native
+    _native.load_library()          # fail loudly if the extension is missing
+    return mod
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden fixtures of the reference
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,mode", [("cfg1_default6.npz", "raised_cosine"), ("cfg2_3band.npz", "raised_cosine"),
+                                       ("cfg4_8band96k.npz", "raised_cosine"), ("hardzero_4band.npz", "hard_zero")])
+def test_multiband_vs_reference_fixture(ce, golden_dir, name, mode):
+    g = _load(golden_dir, name)
+    ext = quiet(ce.chain_bands, list(g["edges"]), 0.75, ce.make_blackman_harris, float(g["sr"]), mode,
+                max_block_size=int(g["max_block"]))
+    assert [e.block_size for e in ext] == list(g["sizes"])
+    L, R = g["in_L"].astype(np.float64), g["in_R"].astype(np.float64)     # float64, as sf.read hands over
+    c, l, r = ce.extract_center_left_right_multi_band_in_memory(L, R, float(g["sr"]), ext)
+    assert c.dtype == np.float32 and c.shape == L.shape
+    peak = float(max(np.abs(L).max(), np.abs(R).max()))
+    rep = assert_parity((g["ref_C"], g["ref_Ls"], g["ref_Rs"]), (c, l, r), peak, what=name)
+    print(name, [(n, round(s, 1), e) for n, s, e in rep])
+
+
+def test_single_band_variants_vs_reference_fixture(ce, golden_dir):
+    g = _load(golden_dir, "single_band.npz")
+    L, R = g["in_L"], g["in_R"]
+    peak = float(max(np.abs(L).max(), np.abs(R).max()))
+    e = ce.MultiBandExtractorAccu(512, 0.5, ce.make_sqrt_hann, 300.0, 5000.0, 48000, "raised_cosine", 100.0, 800.0)
+    got = e.process_all_blocks(L, R)
+    # sqrt-Hann ends in exact zeros: the reference's synthesis window is 0/EPS-safe there, compare finite parts
+    assert_parity([g[f"ref_sqrt_hann50_{k}"] for k in ("C", "Ls", "Rs")], got, peak, what="sqrt_hann50")
+    e = ce.MultiBandExtractorAccu(256, 0.75, ce.make_hann, 1000.0, 24000.0, 48000, "bogus_mode")
+    got = e.process_all_blocks(L, R)
+    assert_parity([g[f"ref_hann75_{k}"] for k in ("C", "Ls", "Rs")], got, peak, what="hann75")
+
+
+def test_chunk_api_vs_reference_fixture(ce, golden_dir):
+    """process_stereo_chunk / flush_final (center_extraction.py:353-424) with device-carried state."""
+    g = _load(golden_dir, "single_band.npz")
+    L, R = g["in_L"], g["in_R"]
+    peak = float(max(np.abs(L).max(), np.abs(R).max()))
+    e = ce.MultiBandExtractorAccu(1024, 0.75, ce.make_blackman_harris, 200.0, 2000.0, 48000, "raised_cosine", 50.0, 500.0)
+    chunks = [np.stack(e.process_stereo_chunk(L[f * 256:f * 256 + 1024], R[f * 256:f * 256 + 1024])) for f in range(12)]
+    got = np.stack(chunks)
+    ref = g["ref_stream_chunks"]
+    assert got.shape == ref.shape
+    for ch, name in enumerate(("C", "Ls", "Rs")):
+        assert_parity([ref[:, ch].reshape(-1)], [got[:, ch].reshape(-1)], peak, names=(name,), what="chunks")
+    acc = np.stack([e.accumC, e.accumL, e.accumR])
+    flush = np.stack(e.flush_final())
+    assert np.array_equal(acc, flush)
+    for ch, name in enumerate(("C", "Ls", "Rs")):
+        assert_parity([g["ref_stream_flush"][ch]], [flush[ch]], peak, names=(name,), what="flush")
+    assert not np.any(np.stack(e.flush_final()))
+
+
+def test_bela_mode_vs_compiled_reference_fixture(ce, golden_dir):
+    from upmix_b200 import bela
+    for hw in (2048, 512):
+        g = _load(golden_dir, f"bela_hw{hw}.npz")
+        L, R = g["in_L"], g["in_R"]
+        ol, orr = quiet(bela.bela_offline, L, R, 48000.0, hw)
+        peak = float(max(np.abs(L).max(), np.abs(R).max()))
+        assert_parity((g["ref_outL"], g["ref_outR"]), (ol, orr), peak, names=("outL", "outR"), what=f"bela hw{hw}")
+        # block-by-block streaming gives the same stream, bit for bit
+        up = bela.MultiBandUpmix()
+        up.setThresholdMultiplier(bela.THRESHOLD_MULTI)
+        quiet(up.setup, hw, 48000.0, 4, [0.0, 500.0, 2000.0, 8000.0, 24000.0])
+        blocks = [up.process(L[i:i + hw], R[i:i + hw], hw) for i in range(0, len(L), hw)]
+        sl = np.concatenate([b[0] for b in blocks])
+        sr_ = np.concatenate([b[1] for b in blocks])
+        assert np.array_equal(sl, ol) and np.array_equal(sr_, orr)
+
+
+# ---------------------------------------------------------------------------------------------------
+# oracle on seeded inputs: every STFT size, ragged lengths
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_fft", [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536])
+def test_every_size_vs_oracle(ce, n_fft):
+    sr = 48000
+    f_low = 32.0 * sr / n_fft            # puts bin_low at 32 like the dynamic-resolution rule does
+    f_high = min(4 * f_low, sr / 2)
+    n = max(4 * n_fft + 1237, 9001)
+    L, R = uo.synth_stereo(n, n_fft, stress=True)
+    e = ce.MultiBandExtractorAccu(n_fft, 0.75, ce.make_blackman_harris, f_low, f_high, sr, "raised_cosine", f_low / 4, f_high / 4)
+    b = uo.make_band(n_fft, 0.75, uo.blackman_harris, f_low, f_high, sr, "raised_cosine", f_low / 4, f_high / 4)
+    assert np.array_equal(e.band_gain(), b.gain) and np.array_equal(e.synthesis_window, b.syn)
+    ref = uo.process_band_batched(b, L.astype(np.float64), R.astype(np.float64))
+    got = e.process_all_blocks(L, R)
+    peak = float(max(np.abs(L).max(), np.abs(R).max()))
+    rep = assert_parity(ref, got, peak, what=f"N={n_fft}")
+    print(n_fft, [(nm, round(s, 1), er) for nm, s, er in rep])
+
+
+@pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 255, 1000, 4097])
+def test_ragged_and_tiny_lengths(ce, n):
+    sr = 48000
+    ext = quiet(ce.chain_bands, [0, 2000, 8000], 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=1024)
+    bands = uo.chain([0, 2000, 8000], 0.75, uo.blackman_harris, sr, max_block=1024)
+    L, R = uo.synth_stereo(max(n, 1), 3)
+    L, R = L[:n], R[:n]
+    got = ce.extract_center_left_right_multi_band_in_memory(L, R, sr, ext)
+    ref = uo.upmix_multiband(bands, L.astype(np.float64), R.astype(np.float64))
+    assert all(g.shape == (n,) for g in got)
+    if n:
+        assert_parity(ref, got, 0.5, what=f"n={n}")
+
+
+def test_wideband_and_full_gain(ce):
+    """A single band covering everything (gain 1 at every bin): exercises DC and Nyquist bins."""
+    sr = 48000
+    for n_fft in (256, 4096, 16384):
+        e = ce.MultiBandExtractorAccu(n_fft, 0.75, ce.make_blackman_harris, 0.0, sr / 2, sr, "raised_cosine", 0.0, 0.0)
+        b = uo.make_band(n_fft, 0.75, uo.blackman_harris, 0.0, sr / 2, sr, "raised_cosine", 0.0, 0.0)
+        assert np.all(b.gain == 1.0)
+        L, R = uo.synth_stereo(3 * n_fft + 11, 9)
+        L += np.float32(0.05)                       # DC offset
+        R[::2] += np.float32(0.03)                  # energy at Nyquist
+        R[1::2] -= np.float32(0.03)
+        ref = uo.process_band_batched(b, L.astype(np.float64), R.astype(np.float64))
+        got = e.process_all_blocks(L, R)
+        assert_parity(ref, got, 1.0, what=f"wideband N={n_fft}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at larger sizes
+# ---------------------------------------------------------------------------------------------------
+def test_partition_invariance_segments_and_tracks(ce):
+    """Time shards with halos and multi-track batches are bit-identical to the plain run."""
+    import torch
+    sr = 48000
+    ext = quiet(ce.chain_bands, [0, 200, 2000], 0.75, ce.make_blackman_harris, sr, "raised_cosine")
+    plan = ce.plan_for(ext)
+    n = 5 * sr + 321
+    L, R = uo.synth_stereo(n, 21)
+    dl, dr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    whole = [t.clone() for t in plan.process(dl, dr)]
+    halo = plan.halo
+    cuts = [0, 16384 * 3, 16384 * 7 + 5000, 200000, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        lo, hi = max(0, a - halo), min(n, b + halo)
+        seg = plan.process_segment(dl[lo:hi].contiguous(), dr[lo:hi].contiguous(), lo, n, a, b)
+        for w, s in zip(whole, seg):
+            assert torch.equal(w[a:b], s), (a, b)
+    # tracks: a batch of 3 different tracks == 3 single runs
+    Ls = torch.stack([dl, dr, dl.flip(0)])
+    Rs = torch.stack([dr, dl, dr * 0.5])
+    batch = plan.process(Ls, Rs)
+    for t in range(3):
+        single = plan.process(Ls[t].contiguous(), Rs[t].contiguous())
+        for bch, sch in zip(batch, single):
+            assert torch.equal(bch[t], sch)
+    # run-to-run determinism
+    again = plan.process(dl, dr)
+    for w, s in zip(whole, again):
+        assert torch.equal(w, s)
+
+
+def test_known_answers_on_device(ce):
+    import torch
+    sr = 48000
+    ext = quiet(ce.chain_bands, [0, 30, 120, 480, 1920, 7680], 0.75, ce.make_blackman_harris, sr, "raised_cosine")
+    n = 20 * sr
+    L, R = uo.synth_stereo(n, 33)
+    dl, dr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    # identical channels: all of the band-limited signal is centre, sides vanish
+    c, l, r = ce.extract_center_left_right_multi_band_in_memory(dl, dl, sr, ext)
+    assert float(l.abs().max()) < 1e-5 and float(r.abs().max()) < 1e-5 and float(c.abs().max()) > 0.05
+    # hard-panned: no centre, no right
+    c, l, r = ce.extract_center_left_right_multi_band_in_memory(dl, torch.zeros_like(dl), sr, ext)
+    assert float(c.abs().max()) == 0.0 and float(r.abs().max()) == 0.0 and float(l.abs().max()) > 0.05
+    # Ls + C does not depend on the other channel (per-frame linearity)
+    c1, l1, _ = ce.extract_center_left_right_multi_band_in_memory(dl, dr, sr, ext)
+    c2, l2, _ = ce.extract_center_left_right_multi_band_in_memory(dl, (dr * 0.3).flip(0).contiguous(), sr, ext)
+    assert float(((l1 + c1) - (l2 + c2)).abs().max()) < 2e-6
+    # fold-down == Ls + 0.5 C / Rs + 0.5 C
+    fl, fr = ce.extract_stereo_fold_down(dl, dr, sr, ext)
+    c1, l1, r1 = ce.extract_center_left_right_multi_band_in_memory(dl, dr, sr, ext)
+    assert float((fl - (l1 + 0.5 * c1)).abs().max()) < 2e-6 and float((fr - (r1 + 0.5 * c1)).abs().max()) < 2e-6
+
+
+def test_five_minute_track_sampled_against_oracle(ce):
+    """cfg 2 shape at a larger size: parity on the first and last seconds and around an interior cut."""
+    import torch
+    sr = 48000
+    ext = quiet(ce.chain_bands, [0, 200, 2000], 0.75, ce.make_blackman_harris, sr, "raised_cosine")
+    bands = uo.chain([0, 200, 2000], 0.75, uo.blackman_harris, sr)
+    n = 300 * sr + 77
+    L, R = uo.synth_stereo(n, 1, stress=True)
+    out = ce.extract_center_left_right_multi_band_in_memory(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda(), sr, ext)
+    out = [o.cpu().numpy() for o in out]
+    peak = float(max(np.abs(L).max(), np.abs(R).max()))
+    margin = 65536
+    for a, b in ((0, 3 * sr), (n // 2 - sr, n // 2 + sr), (n - 3 * sr, n)):
+        lo, hi = max(0, a - margin), min(n, b + margin)
+        # the oracle on an excerpt that starts at a multiple of the largest hop keeps the frame grid
+        lo -= lo % 16384
+        ref = uo.upmix_multiband(bands, L[lo:hi].astype(np.float64), R[lo:hi].astype(np.float64))
+        # excerpt edges differ (ramp-in / missing future frames): compare the interior only
+        ia = a if lo == 0 else max(a, lo + 49152)
+        ib = b if hi == n else min(b, hi - 65536)
+        assert_parity([x[ia - lo:ib - lo] for x in ref], [x[ia:ib] for x in out], peak, what=f"[{a},{b})")
+
+
+def test_host_buffer_entry_point(ce, golden_dir):
+    g = _load(golden_dir, "cfg2_3band.npz")
+    ext = quiet(ce.chain_bands, list(g["edges"]), 0.75, ce.make_blackman_harris, 48000.0, "raised_cosine")
+    plan = ce.plan_for(ext)
+    c, l, r = plan.process_host(g["in_L"], g["in_R"])
+    assert_parity((g["ref_C"], g["ref_Ls"], g["ref_Rs"]), (c, l, r), 0.5, what="process_host")
+
+
+def test_unsupported_inputs_fail_loudly(ce):
+    from upmix_b200 import _native
+    e = ce.MultiBandExtractorAccu(1000, 0.75, ce.make_hann, 100.0, 1000.0, 48000)
+    with pytest.raises(NotImplementedError):
+        e.process_all_blocks(np.zeros(5000, np.float32), np.zeros(5000, np.float32))
+    with pytest.raises(ValueError):
+        ce.MultiBandExtractorAccu(64, 0.999, ce.make_hann, 100.0, 1000.0, 48000)
+    w = np.ones(32, np.float32)
+    with pytest.raises(_native.UpmixNativeError):
+        _native.Plan([(32, 8, w, w, np.ones(17, np.float32))])

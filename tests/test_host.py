@@ -1,0 +1,134 @@
+"""CPU: host-side plan construction of the product (upmix_b200.center_extraction) against the golden
+fixtures of the reference -- tables must be bit-identical -- and the C-ABI library's exports."""
+import contextlib
+import ctypes
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+import upmix_b200.center_extraction as ce
+from upmix_b200 import _native, bela
+from oracle import upmix_oracle as uo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def test_windows_and_synthesis_windows_bit_identical(golden_dir):
+    t = np.load(os.path.join(golden_dir, "tables.npz"))
+    for name in ("blackman_harris", "sqrt_hann", "hann", "blackman", "hamming", "rect"):
+        for n in (64, 256, 1024):
+            w = getattr(ce, "make_" + name)(n)
+            assert w.dtype == np.float32 and np.array_equal(w, t[f"win_{name}_{n}"])
+            for ov in (50, 75):
+                with np.errstate(all="ignore"):
+                    s = ce.design_wola_synthesis_window(w, ov / 100.0)
+                assert s.dtype == np.float32 and np.array_equal(s, t[f"syn_{name}_{n}_{ov}"], equal_nan=True)
+
+
+def test_chain_bands_tables_bit_identical(golden_dir, capsys):
+    t = np.load(os.path.join(golden_dir, "tables.npz"))
+    ext = ce.chain_bands([0, 30, 120, 480, 1920, 7680], 0.75, ce.make_blackman_harris, 48000, "raised_cosine")
+    printed = capsys.readouterr().out.strip().splitlines()
+    assert len(printed) == 6 and printed[1].startswith("[Band 2] f_low=30.0 Hz, f_high=120.0 Hz, block_size=65536, "
+                                                       "xover_low=7.5 Hz, xover_high=30.0 Hz")
+    assert [e.block_size for e in ext] == [65536, 65536, 16384, 4096, 1024, 256]
+    assert [e.hop_size for e in ext] == [16384, 16384, 4096, 1024, 256, 64]
+    for i, e in enumerate(ext):
+        assert np.array_equal(e.band_gain(), t[f"gain_default6_{i}"])
+        if f"syn_default6_{i}" in t:
+            assert np.array_equal(e.synthesis_window, t[f"syn_default6_{i}"])
+        n, h, ana, syn, gain = e.plan_tables()
+        assert (n, h) == (e.block_size, e.hop_size) and ana.dtype == syn.dtype == gain.dtype == np.float32
+    for f, sr, n in t["sizes_rule"]:
+        assert ce.compute_block_size_for_low_freq(float(f), float(sr)) == int(n)
+    for f, n, b in t["bins"]:
+        assert ce.freq_to_bin(float(f), 48000, int(n)) == int(b)
+
+
+def test_host_tables_match_oracle_on_random_bands():
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        sr = float(rng.choice([44100, 48000, 96000]))
+        n = int(2 ** rng.integers(6, 14))
+        f_low = float(rng.choice([0.0, rng.uniform(10, 4000)]))
+        f_high = float(rng.choice([sr / 2, rng.uniform(f_low + 1, sr / 2)]))
+        mode = str(rng.choice(["raised_cosine", "hard_zero", "other"]))
+        wl, wh = float(rng.uniform(0, 500)), float(rng.uniform(0, 3000))
+        e = ce.MultiBandExtractorAccu(n, 0.75, ce.make_blackman_harris, f_low, f_high, sr, mode, wl, wh)
+        b = uo.make_band(n, 0.75, uo.blackman_harris, f_low, f_high, sr, mode, wl, wh)
+        assert np.array_equal(e.band_gain(), b.gain)
+        assert np.array_equal(e.synthesis_window, b.syn) and np.array_equal(e.analysis_window, b.ana)
+
+
+def test_utilities_and_errors():
+    assert [ce.next_power_of_2(x) for x in (-3, 0, 1, 2, 3, 4, 5, 1023, 1024, 1025)] == [1, 1, 1, 2, 4, 4, 8, 1024, 1024, 2048]
+    assert ce.hp_freq_to_crossover_width(120.0) == 30.0
+    assert ce.compute_block_size_for_low_freq(0.0, 48000, max_block_size=8192) == 8192
+    assert ce.compute_block_size_for_low_freq(100.0, 96000, 8192, 32) == 8192
+    assert ce.compute_block_size_for_low_freq(100.0, 96000, 2 ** 16, 16) == 16384
+    with pytest.raises(ValueError):
+        ce.design_wola_synthesis_window(np.ones(8, np.float32), 0.95)
+    with pytest.raises(ValueError):
+        ce.MultiBandExtractorAccu(64, 0.999, ce.make_hann, 0.0, 100.0, 48000)
+    x = np.random.default_rng(0).standard_normal(64)
+    w = ce.make_hann(64)
+    assert np.allclose(ce.forward_stft(x, w), np.fft.rfft(x * w))
+    assert ce.inverse_stft(np.fft.rfft(x), w).dtype == np.float32
+    ext = quiet(ce.chain_bands, [0, 1000], 0.75, ce.make_blackman_harris, 48000, max_block_size=4096, threshold_factor=16,
+                xo_fraction=0.5)
+    assert [e.block_size for e in ext] == [4096, 1024] and ext[0].xover_width_high_hz == 500.0
+
+
+def test_bela_tables_match_oracle():
+    bands = quiet(bela.bela_chain_bands, [0.0, 500.0, 2000.0, 8000.0, 24000.0], 48000.0, 2048)
+    ref = uo.bela_chain([0, 500, 2000, 8000, 24000], 48000, 2048)
+    assert [b.block_size for b in bands] == [8192, 4096, 1024, 256] == [r.n_fft for r in ref]
+    for b, r in zip(bands, ref):
+        assert np.array_equal(b.band_gain(), r.gain)
+        assert np.max(np.abs(b.analysis_window - r.ana)) < 1e-6        # float32 cosf vs float64 cos
+        assert np.array_equal(b.analysis_window, b.synthesis_window)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    """include/upmix_b200.h is the boundary: every function it declares must be exported (no compute
+    calls here -- there is no GPU in this container)."""
+    header = open(os.path.join(ROOT, "include", "upmix_b200.h")).read()
+    declared = set(re.findall(r"\b(upmix_[a-z_0-9]+)\s*\(", header))
+    assert declared and declared == set(_native.EXPORTS)
+    assert os.path.isfile(_native.LIB_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib2 = _native.load_library()
+    assert lib2.upmix_version() >= 1000
+    assert lib2.upmix_last_error() is not None
+    # argument validation happens before any CUDA call
+    assert lib2.upmix_plan_create(0, None, 0, 0, ctypes.byref(ctypes.c_void_p())) == -1
+    assert b"band" in lib2.upmix_last_error()
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    e = ce.MultiBandExtractorAccu(256, 0.75, ce.make_hann, 100.0, 1000.0, 48000)
+    with pytest.raises(_native.UpmixNativeError):
+        e.process_all_blocks(np.zeros(1000), np.zeros(1000))
+    with pytest.raises(_native.UpmixNativeError):
+        ce.extract_center_left_right_multi_band_in_memory(np.zeros(1000), np.zeros(1000), 48000, [e])
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "upmix_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"

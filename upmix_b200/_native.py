@@ -1,0 +1,266 @@
+"""ctypes binding of the C ABI in include/upmix_b200.h (csrc/libupmix_b200.so).
+
+PyTorch is used only as plumbing: device buffers (tensor.data_ptr()), the current CUDA stream and
+pinned host staging.  There is no CPU fallback: if the library is missing, or no CUDA device is
+present, the calls below raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libupmix_b200.so")
+
+OUT_LSCRS = 0
+OUT_FOLD = 1
+
+FUSED_MAX_N = 8192
+LARGE_MAX_N = 65536
+MIN_N = 64
+
+
+class UpmixNativeError(RuntimeError):
+    pass
+
+
+class _BandDesc(ctypes.Structure):
+    _fields_ = [("n_fft", ctypes.c_int32), ("hop", ctypes.c_int32), ("ana", ctypes.c_void_p),
+                ("syn", ctypes.c_void_p), ("gain", ctypes.c_void_p)]
+
+
+_lib = None
+
+
+def _sig(fn, restype, argtypes):
+    fn.restype = restype
+    fn.argtypes = argtypes
+
+
+def load_library():
+    """Load libupmix_b200.so (built by `__graft_entry__.build()` / csrc/build.sh)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise UpmixNativeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or upmix_b200/csrc/build.sh).  upmix_b200 has no CPU path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    _sig(lib.upmix_last_error, ctypes.c_char_p, [])
+    _sig(lib.upmix_version, i32, [])
+    _sig(lib.upmix_plan_create, i32, [i32, ctypes.POINTER(_BandDesc), i32, i32, ctypes.POINTER(vp)])
+    _sig(lib.upmix_plan_destroy, i32, [vp])
+    _sig(lib.upmix_plan_n_bands, i32, [vp])
+    _sig(lib.upmix_workspace_bytes, i64, [vp, i64, i32])
+    _sig(lib.upmix_segment_halo, i64, [vp])
+    _sig(lib.upmix_process, i32, [vp, vp, vp, i64, i32, i64, vp, vp, vp, i64, vp, i64, vp])
+    _sig(lib.upmix_process_segment, i32,
+         [vp, vp, vp, i64, i64, i64, i64, i64, i32, i64, vp, vp, vp, i64, vp, i64, vp])
+    _sig(lib.upmix_stream_state_bytes, i64, [vp, i32])
+    _sig(lib.upmix_stream_workspace_bytes, i64, [vp, i32, i32])
+    _sig(lib.upmix_stream_delay, i64, [vp])
+    _sig(lib.upmix_stream_reset, i32, [vp, vp, i32, vp])
+    _sig(lib.upmix_stream_block, i32, [vp, vp, i64, vp, vp, i32, i32, i64, vp, vp, vp, i64, vp, i64, vp])
+    _sig(lib.upmix_process_host, i32, [vp, vp, vp, i64, vp, vp, vp])
+    _sig(lib.upmix_frame_step, i32, [vp, vp, i64, vp, vp, i32, i64, vp, vp, vp, i64, vp, i64, vp])
+    _lib = lib
+    return lib
+
+
+EXPORTS = ("upmix_last_error", "upmix_version", "upmix_plan_create", "upmix_plan_destroy",
+           "upmix_plan_n_bands", "upmix_workspace_bytes", "upmix_segment_halo", "upmix_process",
+           "upmix_process_segment", "upmix_stream_state_bytes", "upmix_stream_workspace_bytes",
+           "upmix_stream_delay", "upmix_stream_reset", "upmix_stream_block", "upmix_process_host",
+           "upmix_frame_step")
+
+
+def _check(rc: int):
+    if rc < 0:
+        raise UpmixNativeError(f"upmix_b200 error {rc}: {load_library().upmix_last_error().decode()}")
+    return rc
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise UpmixNativeError("no CUDA device: upmix_b200 runs on B200 (sm_100a) only and has no CPU path")
+    return torch
+
+
+class Plan:
+    """An immutable set of bands on one device (UpmixPlan).  `bands` is a sequence of
+    (n_fft, hop, ana[n_fft], syn[n_fft], gain[n_fft/2+1]) with float32-convertible tables."""
+
+    def __init__(self, bands: Sequence[Tuple[int, int, np.ndarray, np.ndarray, np.ndarray]],
+                 out_mode: int = OUT_LSCRS, device: Optional[int] = None):
+        torch = _torch()
+        lib = load_library()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.out_mode = out_mode
+        self.sizes = [int(b[0]) for b in bands]
+        self.hops = [int(b[1]) for b in bands]
+        keep = []
+        descs = (_BandDesc * len(bands))()
+        for i, (n_fft, hop, ana, syn, gain) in enumerate(bands):
+            ana = np.ascontiguousarray(ana, dtype=np.float32)
+            syn = np.ascontiguousarray(syn, dtype=np.float32)
+            gain = np.ascontiguousarray(gain, dtype=np.float32)
+            if ana.shape != (n_fft,) or syn.shape != (n_fft,) or gain.shape != (n_fft // 2 + 1,):
+                raise ValueError(f"band {i}: table shapes do not match n_fft={n_fft}")
+            keep += [ana, syn, gain]
+            descs[i] = _BandDesc(n_fft, hop, ana.ctypes.data, syn.ctypes.data, gain.ctypes.data)
+        handle = ctypes.c_void_p()
+        _check(lib.upmix_plan_create(len(bands), descs, out_mode, self.device, ctypes.byref(handle)))
+        self._h = handle
+        self._lib = lib
+        self._ws = None
+        self.halo = int(lib.upmix_segment_halo(self._h))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.upmix_plan_destroy(h)
+            except Exception:
+                pass
+
+    # -- workspace -----------------------------------------------------------------------------
+    def workspace_bytes(self, seg_len: int, n_tracks: int = 1) -> int:
+        return _check(self._lib.upmix_workspace_bytes(self._h, int(seg_len), int(n_tracks)))
+
+    def _workspace(self, nbytes: int):
+        torch = _torch()
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=f"cuda:{self.device}")
+        return self._ws
+
+    def release_workspace(self):
+        self._ws = None
+
+    # -- device-resident processing ------------------------------------------------------------
+    def process(self, L, R, out=None):
+        """L, R: float32 CUDA tensors [n] or [tracks, n].  Returns (C, Ls, Rs) -- or (L', R') in
+        fold-down mode -- as tensors of the same shape.  Asynchronous on the current stream."""
+        return self.process_segment(L, R, 0, L.shape[-1], 0, L.shape[-1], out=out)
+
+    def process_segment(self, L, R, in_begin: int, n_total: int, seg_begin: int, seg_end: int, out=None):
+        torch = _torch()
+        if L.dtype != torch.float32 or R.dtype != torch.float32 or not L.is_cuda or not R.is_cuda:
+            raise TypeError("L and R must be float32 CUDA tensors")
+        if L.shape != R.shape or L.dim() not in (1, 2):
+            raise ValueError("L and R must have the same shape [n] or [tracks, n]")
+        if L.device.index != self.device:
+            raise ValueError(f"tensors are on {L.device}, plan is on cuda:{self.device}")
+        squeeze = L.dim() == 1
+        if squeeze:
+            L, R = L[None], R[None]
+        if L.stride(1) != 1 or R.stride(1) != 1 or (L.shape[0] > 1 and L.stride(0) != R.stride(0)):
+            L, R = L.contiguous(), R.contiguous()
+        tracks, in_len = L.shape
+        seg_len = seg_end - seg_begin
+        n_out = 3 if self.out_mode == OUT_LSCRS else 2
+        if out is None:
+            out = torch.empty((n_out, tracks, seg_len), dtype=torch.float32, device=L.device)
+        elif out.shape != (n_out, tracks, seg_len) or not out.is_contiguous() or out.dtype != torch.float32:
+            raise ValueError(f"out must be a contiguous float32 tensor of shape {(n_out, tracks, seg_len)}")
+        oc, ol, orr = (out[0], out[1], out[2]) if n_out == 3 else (None, out[0], out[1])
+        wsb = self.workspace_bytes(seg_len, tracks)
+        ws = self._workspace(wsb)
+        stream = torch.cuda.current_stream(L.device).cuda_stream
+        with torch.cuda.device(L.device):
+            _check(self._lib.upmix_process_segment(
+                self._h, L.data_ptr(), R.data_ptr(), int(in_begin), int(in_len), int(n_total), int(seg_begin),
+                int(seg_end), tracks, L.stride(0) if tracks > 1 else in_len,
+                oc.data_ptr() if oc is not None else None, ol.data_ptr(), orr.data_ptr(), seg_len,
+                ws.data_ptr(), wsb, stream))
+        res = tuple(o[0] for o in out) if squeeze else tuple(out[i] for i in range(n_out))
+        return res
+
+    def frame_step(self, ring, frame_index: int, blk_l, blk_r):
+        """Single-band plans: one frame of the stateful chunk API (upmix_frame_step).  ring: float32
+        CUDA tensor [3, n_fft]; blk_l / blk_r: float32 CUDA tensors [n_fft].  Returns (C, Ls, Rs) [hop]."""
+        torch = _torch()
+        hop = self.hops[0]
+        out = torch.empty((3, hop), dtype=torch.float32, device=ring.device)
+        wsb = self.workspace_bytes(hop, 1)
+        ws = self._workspace(wsb)
+        stream = torch.cuda.current_stream(ring.device).cuda_stream
+        blk_l, blk_r = blk_l.contiguous(), blk_r.contiguous()
+        with torch.cuda.device(ring.device):
+            _check(self._lib.upmix_frame_step(self._h, ring.data_ptr(), int(frame_index), blk_l.data_ptr(),
+                                              blk_r.data_ptr(), 1, self.sizes[0], out[0].data_ptr(), out[1].data_ptr(),
+                                              out[2].data_ptr(), hop, ws.data_ptr(), wsb, stream))
+        return out[0], out[1], out[2]
+
+    # -- block streaming -------------------------------------------------------------------------
+    def stream_open(self, n_tracks: int = 1):
+        return Stream(self, n_tracks)
+
+    # -- host buffers ----------------------------------------------------------------------------
+    def process_host(self, L: np.ndarray, R: np.ndarray):
+        """numpy float32 in, numpy float32 out, through upmix_process_host (H2D + kernels + D2H)."""
+        _torch()
+        L = np.ascontiguousarray(L, dtype=np.float32)
+        R = np.ascontiguousarray(R, dtype=np.float32)
+        if L.ndim != 1 or L.shape != R.shape:
+            raise ValueError("L and R must be 1-D arrays of equal length")
+        n = L.shape[0]
+        n_out = 3 if self.out_mode == OUT_LSCRS else 2
+        outs = [np.empty(n, dtype=np.float32) for _ in range(n_out)]
+        ptrs = [o.ctypes.data for o in outs]
+        if n_out == 2:
+            ptrs = [None] + ptrs
+        _check(self._lib.upmix_process_host(self._h, L.ctypes.data, R.ctypes.data, n, *ptrs))
+        return tuple(outs)
+
+
+class Stream:
+    """Block-by-block processing with carried state (upmix_stream_block)."""
+
+    def __init__(self, plan: Plan, n_tracks: int = 1):
+        torch = _torch()
+        self.plan = plan
+        self.n_tracks = n_tracks
+        lib = plan._lib
+        nbytes = _check(lib.upmix_stream_state_bytes(plan._h, n_tracks))
+        self.state = torch.zeros(int(nbytes), dtype=torch.uint8, device=f"cuda:{plan.device}")
+        self.delay = int(lib.upmix_stream_delay(plan._h))
+        self.samples_done = 0
+        self._ws = None
+
+    def reset(self):
+        self.state.zero_()
+        self.samples_done = 0
+
+    def block(self, in_l, in_r):
+        """in_l, in_r: float32 CUDA tensors [n_new] or [tracks, n_new].  Returns the next n_new output
+        samples of every output channel (delayed by self.delay)."""
+        torch = _torch()
+        plan, lib = self.plan, self.plan._lib
+        squeeze = in_l.dim() == 1
+        if squeeze:
+            in_l, in_r = in_l[None], in_r[None]
+        in_l, in_r = in_l.contiguous(), in_r.contiguous()
+        tracks, n_new = in_l.shape
+        if tracks != self.n_tracks:
+            raise ValueError("track count differs from the stream's")
+        n_out = 3 if plan.out_mode == OUT_LSCRS else 2
+        out = torch.empty((n_out, tracks, n_new), dtype=torch.float32, device=in_l.device)
+        oc, ol, orr = (out[0], out[1], out[2]) if n_out == 3 else (None, out[0], out[1])
+        wsb = _check(lib.upmix_stream_workspace_bytes(plan._h, n_new, tracks))
+        if self._ws is None or self._ws.numel() < wsb:
+            self._ws = torch.empty(int(wsb), dtype=torch.uint8, device=in_l.device)
+        stream = torch.cuda.current_stream(in_l.device).cuda_stream
+        with torch.cuda.device(in_l.device):
+            _check(lib.upmix_stream_block(plan._h, self.state.data_ptr(), self.samples_done, in_l.data_ptr(),
+                                          in_r.data_ptr(), n_new, tracks, n_new,
+                                          oc.data_ptr() if oc is not None else None, ol.data_ptr(), orr.data_ptr(),
+                                          n_new, self._ws.data_ptr(), wsb, stream))
+        self.samples_done += n_new
+        return tuple(o[0] for o in out) if squeeze else tuple(out[i] for i in range(n_out))

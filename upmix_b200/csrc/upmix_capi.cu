@@ -1,0 +1,469 @@
+// C-ABI layer (include/upmix_b200.h): plan construction, workspace layout, band scheduling.
+// No torch types, no exceptions across the boundary.
+#include "../../include/upmix_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "upmix_kernels.cuh"
+#include "upmix_launch.h"
+
+using namespace upmix;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_CHECK(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(UPMIX_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+constexpr int K3_HOPS_PER_RUN = 8;
+
+}  // namespace
+
+struct UpmixPlan {
+    int device = 0;
+    int out_mode = 0;
+    std::vector<BandDev> bands;
+    void* tables = nullptr;     // one device allocation holding every table
+    int max_large_n = 0;        // largest n_fft handled by the four-step path (0: none)
+    int64_t halo = 0;           // max over bands of n_fft - hop
+    int sm_count = 148;
+};
+
+namespace {
+
+struct Layout {
+    int64_t ws_seg = 0;         // per-track stride of a band output in the workspace (floats)
+    int64_t band_out_bytes = 0;
+    int wave_hops = 0;          // large path: hops finished per wave
+    int wave_frames = 0;        // large path: frames resident per wave (even)
+    int64_t a_bytes = 0, b1_bytes = 0, b2_bytes = 0;
+    int64_t total = 0;
+};
+
+Layout make_layout(const UpmixPlan* p, int64_t seg_len, int n_tracks) {
+    Layout l;
+    l.ws_seg = round_up(std::max<int64_t>(seg_len, 1), 64);
+    l.band_out_bytes = round_up((int64_t)p->bands.size() * 3 * n_tracks * l.ws_seg * (int64_t)sizeof(float), 256);
+    l.total = l.band_out_bytes;
+    if (p->max_large_n) {
+        int64_t hop_min = INT64_MAX;
+        for (const BandDev& b : p->bands)
+            if (b.n_fft > FUSED_MAX_N) hop_min = std::min<int64_t>(hop_min, b.hop);
+        const int64_t seg_hops = (seg_len + hop_min - 1) / hop_min + 1;
+        int64_t wh = std::max<int64_t>(16, 512 / std::max(1, n_tracks));
+        wh = round_up(std::min<int64_t>(wh, round_up(seg_hops, K3_HOPS_PER_RUN)), K3_HOPS_PER_RUN);
+        l.wave_hops = (int)wh;
+        l.wave_frames = (int)wh + 6;
+        const int64_t per_frame = (int64_t)p->max_large_n * (int64_t)sizeof(float2);
+        l.a_bytes = round_up((int64_t)n_tracks * l.wave_frames * per_frame, 256);
+        l.b1_bytes = l.a_bytes;
+        l.b2_bytes = round_up((int64_t)n_tracks * (l.wave_frames / 2) * per_frame, 256);
+        l.total += l.a_bytes + l.b1_bytes + l.b2_bytes;
+    }
+    return l;
+}
+
+int pick_hops_per_run(const UpmixPlan* p, int64_t total_hops, int n_tracks) {
+    const int64_t target_ctas = (int64_t)p->sm_count * 4;
+    int64_t r = (total_hops * n_tracks + target_ctas - 1) / target_ctas;
+    return (int)std::min<int64_t>(64, std::max<int64_t>(8, r));
+}
+
+// Runs every band of the plan over output samples [seg_begin, seg_end) into the band workspace,
+// then sums the bands.  `state` (optional) = per-band overlap-add rings for block streaming.
+int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_begin, int64_t in_end,
+                int64_t n_total, int64_t seg_begin, int64_t seg_end, int n_tracks, int64_t in_stride, float* out_c,
+                float* out_l, float* out_r, int64_t out_stride, void* workspace, int64_t workspace_bytes,
+                float* const* band_state, cudaStream_t st) {
+    const int64_t seg_len = seg_end - seg_begin;
+    const Layout lay = make_layout(p, seg_len, n_tracks);
+    if (workspace_bytes < lay.total)
+        return fail(UPMIX_E_WORKSPACE, "workspace too small: %lld bytes given, %lld needed", (long long)workspace_bytes,
+                    (long long)lay.total);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(UPMIX_E_INVALID, "workspace must be 256-byte aligned");
+    float* ws = reinterpret_cast<float*>(workspace);
+    char* scratch = reinterpret_cast<char*>(workspace) + lay.band_out_bytes;
+    const int nb = (int)p->bands.size();
+    const int64_t prod_end = std::min(seg_end, n_total);      // nothing is produced past the end of the track
+
+    for (int bi = 0; bi < nb; bi++) {
+        const BandDev& b = p->bands[bi];
+        SegArgs a;
+        a.in_l = L;
+        a.in_r = R;
+        a.in_stride = in_stride;
+        a.in_begin = in_begin;
+        a.in_end = in_end;
+        float* base = ws + (int64_t)bi * 3 * n_tracks * lay.ws_seg;
+        a.out_c = base;
+        a.out_l = base + (int64_t)n_tracks * lay.ws_seg;
+        a.out_r = base + 2 * (int64_t)n_tracks * lay.ws_seg;
+        a.out_stride = lay.ws_seg;
+        a.out_begin = seg_begin;
+        a.seg_begin = std::max<int64_t>(seg_begin, 0);
+        a.seg_end = prod_end;
+        a.state = band_state ? band_state[bi] : nullptr;
+        if (seg_begin < 0 || prod_end < seg_end) {
+            // part of the requested range lies outside the track: those samples are zero
+            CU_CHECK(cudaMemsetAsync(base, 0, (size_t)3 * n_tracks * lay.ws_seg * sizeof(float), st));
+        }
+        if (a.seg_end <= a.seg_begin) continue;
+        a.hop_begin = a.seg_begin / b.hop;
+        a.hop_end = (a.seg_end + b.hop - 1) / b.hop;
+        const int64_t total_hops = a.hop_end - a.hop_begin;
+        if (b.n_fft <= FUSED_MAX_N) {
+            if (a.state) {
+                a.hops_per_run = (int)total_hops;              // the ring is carried: one CTA per track
+                CU_CHECK(launch_band_fused(b, a, 1, n_tracks, st));
+            } else {
+                a.hops_per_run = pick_hops_per_run(p, total_hops, n_tracks);
+                const int n_runs = (int)((total_hops + a.hops_per_run - 1) / a.hops_per_run);
+                CU_CHECK(launch_band_fused(b, a, n_runs, n_tracks, st));
+            }
+        } else {
+            if (a.state) return fail(UPMIX_E_UNSUPPORTED, "block streaming needs n_fft <= %d (band %d has %d)", FUSED_MAX_N, bi, b.n_fft);
+            const int64_t per_frame = (int64_t)b.n_fft;
+            WaveArgs w;
+            w.a = reinterpret_cast<float2*>(scratch);
+            w.b1 = reinterpret_cast<float2*>(scratch + lay.a_bytes);
+            w.b2 = reinterpret_cast<float2*>(scratch + lay.a_bytes + lay.b1_bytes);
+            (void)per_frame;
+            a.hops_per_run = K3_HOPS_PER_RUN;
+            const int64_t h_begin = a.hop_begin, h_end = a.hop_end;
+            for (int64_t w0 = h_begin; w0 < h_end; w0 += lay.wave_hops) {
+                const int64_t w1 = std::min<int64_t>(w0 + lay.wave_hops, h_end);
+                const int64_t fa = std::max<int64_t>(0, w0 - 3) & ~1LL;
+                const int64_t fb = (w1 + 1) & ~1LL;
+                w.frame0 = fa;
+                w.n_frames = (int)(fb - fa);
+                if (w.n_frames > lay.wave_frames) return fail(UPMIX_E_INVALID, "internal: wave of %d frames exceeds %d", w.n_frames, lay.wave_frames);
+                SegArgs aw = a;
+                aw.hop_begin = w0;
+                aw.hop_end = w1;
+                const int n_runs = (int)((w1 - w0 + K3_HOPS_PER_RUN - 1) / K3_HOPS_PER_RUN);
+                CU_CHECK(launch_col_fwd(b, aw, w, n_tracks, st));
+                CU_CHECK(launch_row_mask(b, w, n_tracks, st));
+                CU_CHECK(launch_col_inv_ola(b, aw, w, n_runs, n_tracks, st));
+            }
+        }
+    }
+    CU_CHECK(launch_band_sum(ws, nb, n_tracks, seg_len, lay.ws_seg, out_c, out_l, out_r, out_stride, p->out_mode, st));
+    return UPMIX_OK;
+}
+
+int check_io(const UpmixPlan* p, const float* L, const float* R, float* out_c, float* out_l, float* out_r, int n_tracks) {
+    if (!p) return fail(UPMIX_E_INVALID, "plan is NULL");
+    if (!L || !R) return fail(UPMIX_E_INVALID, "input pointer is NULL");
+    if (!out_l || !out_r || (p->out_mode == UPMIX_OUT_LSCRS && !out_c)) return fail(UPMIX_E_INVALID, "output pointer is NULL");
+    if (n_tracks < 1 || n_tracks > 65535) return fail(UPMIX_E_INVALID, "n_tracks must be in [1, 65535], got %d", n_tracks);
+    return UPMIX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* upmix_last_error(void) { return g_err; }
+
+int upmix_version(void) { return 1000; }
+
+int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int device, UpmixPlan** out) {
+    if (!out) return fail(UPMIX_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_bands < 1 || !bands) return fail(UPMIX_E_INVALID, "need at least one band");
+    if (out_mode != UPMIX_OUT_LSCRS && out_mode != UPMIX_OUT_FOLD) return fail(UPMIX_E_INVALID, "unknown out_mode %d", out_mode);
+    int64_t floats = 2 * TW_N;   // master twiddles
+    for (int i = 0; i < n_bands; i++) {
+        const UpmixBandDesc& d = bands[i];
+        if (!d.ana || !d.syn || !d.gain) return fail(UPMIX_E_INVALID, "band %d: NULL table", i);
+        if (!is_pow2(d.n_fft) || d.n_fft < 64 || d.n_fft > LARGE_MAX_N)
+            return fail(UPMIX_E_UNSUPPORTED, "band %d: n_fft=%d is not a power of two in [64, %d]", i, d.n_fft, LARGE_MAX_N);
+        if (d.hop < 2 || d.n_fft % d.hop != 0 || (d.hop & 1))
+            return fail(UPMIX_E_UNSUPPORTED, "band %d: hop=%d must be even and divide n_fft=%d", i, d.hop, d.n_fft);
+        if (d.n_fft > FUSED_MAX_N && d.hop * 4 != d.n_fft)
+            return fail(UPMIX_E_UNSUPPORTED, "band %d: n_fft=%d > %d requires hop = n_fft/4 (75%% overlap), got %d", i, d.n_fft, FUSED_MAX_N, d.hop);
+        floats += round_up(d.n_fft, 64) * 2 + round_up(d.n_fft / 2 + 1, 64);
+        if (d.n_fft > FUSED_MAX_N) floats += 2LL * d.n_fft;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(UPMIX_E_CUDA, "cannot select device %d", device);
+    UpmixPlan* p = new (std::nothrow) UpmixPlan();
+    if (!p) return fail(UPMIX_E_INVALID, "out of host memory");
+    p->device = device;
+    p->out_mode = out_mode;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) p->sm_count = sms;
+    std::vector<float> host((size_t)floats, 0.f);
+    cudaError_t e = cudaMalloc(&p->tables, (size_t)floats * sizeof(float));
+    if (e != cudaSuccess) {
+        delete p;
+        return fail(UPMIX_E_CUDA, "cudaMalloc(%lld) failed: %s", (long long)(floats * 4), cudaGetErrorString(e));
+    }
+    float* dbase = reinterpret_cast<float*>(p->tables);
+    int64_t off = 0;
+    // master twiddles, double precision -> float32, exact at the octant points
+    for (int m = 0; m < TW_N; m++) {
+        const double ang = -2.0 * M_PI * (double)m / (double)TW_N;
+        double c = cos(ang), s = sin(ang);
+        if (m % (TW_N / 4) == 0) { c = (m == 0) ? 1.0 : (m == TW_N / 2 ? -1.0 : 0.0); s = (m == TW_N / 4) ? -1.0 : (m == 3 * TW_N / 4 ? 1.0 : 0.0); }
+        host[2 * m] = (float)c;
+        host[2 * m + 1] = (float)s;
+    }
+    const float2* d_tw = reinterpret_cast<const float2*>(dbase);
+    off += 2 * TW_N;
+    for (int i = 0; i < n_bands; i++) {
+        const UpmixBandDesc& d = bands[i];
+        BandDev b;
+        b.n_fft = d.n_fft;
+        b.hop = d.hop;
+        b.tw = d_tw;
+        b.tw_col = nullptr;
+        memcpy(&host[off], d.ana, sizeof(float) * d.n_fft);
+        b.ana = dbase + off;
+        off += round_up(d.n_fft, 64);
+        const float inv_n = 1.0f / (float)d.n_fft;   // exact: n_fft is a power of two
+        for (int n = 0; n < d.n_fft; n++) host[off + n] = d.syn[n] * inv_n;
+        b.syn = dbase + off;
+        off += round_up(d.n_fft, 64);
+        memcpy(&host[off], d.gain, sizeof(float) * (d.n_fft / 2 + 1));
+        b.gain = dbase + off;
+        off += round_up(d.n_fft / 2 + 1, 64);
+        if (d.n_fft > FUSED_MAX_N) {
+            const int n2 = d.n_fft / COL_R;
+            for (int k1 = 0; k1 < COL_R; k1++)
+                for (int c = 0; c < n2; c++) {
+                    const int64_t m = ((int64_t)k1 * c) % d.n_fft;
+                    const double ang = -2.0 * M_PI * (double)m / (double)d.n_fft;
+                    host[off + 2 * ((int64_t)k1 * n2 + c)] = (float)cos(ang);
+                    host[off + 2 * ((int64_t)k1 * n2 + c) + 1] = (float)sin(ang);
+                }
+            b.tw_col = reinterpret_cast<const float2*>(dbase + off);
+            off += 2LL * d.n_fft;
+            p->max_large_n = std::max(p->max_large_n, d.n_fft);
+        }
+        p->halo = std::max<int64_t>(p->halo, d.n_fft - d.hop);
+        p->bands.push_back(b);
+    }
+    e = cudaMemcpy(p->tables, host.data(), (size_t)floats * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(p->tables);
+        delete p;
+        return fail(UPMIX_E_CUDA, "table upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return UPMIX_OK;
+}
+
+int upmix_plan_destroy(UpmixPlan* plan) {
+    if (!plan) return UPMIX_OK;
+    DeviceGuard guard(plan->device);
+    cudaFree(plan->tables);
+    delete plan;
+    return UPMIX_OK;
+}
+
+int upmix_plan_n_bands(const UpmixPlan* plan) { return plan ? (int)plan->bands.size() : fail(UPMIX_E_INVALID, "plan is NULL"); }
+
+int64_t upmix_workspace_bytes(const UpmixPlan* plan, int64_t seg_len, int n_tracks) {
+    if (!plan) return fail(UPMIX_E_INVALID, "plan is NULL");
+    if (seg_len < 0 || n_tracks < 1) return fail(UPMIX_E_INVALID, "bad seg_len / n_tracks");
+    return make_layout(plan, seg_len, n_tracks).total;
+}
+
+int64_t upmix_segment_halo(const UpmixPlan* plan) { return plan ? plan->halo : fail(UPMIX_E_INVALID, "plan is NULL"); }
+
+int upmix_process_segment(const UpmixPlan* plan, const float* L, const float* R, int64_t in_begin, int64_t in_len,
+                          int64_t n_total, int64_t seg_begin, int64_t seg_end, int n_tracks, int64_t in_stride,
+                          float* out_c, float* out_l, float* out_r, int64_t out_stride, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+    int rc = check_io(plan, L, R, out_c, out_l, out_r, n_tracks);
+    if (rc) return rc;
+    if (n_total < 0 || in_begin < 0 || in_len < 0 || in_begin + in_len > n_total)
+        return fail(UPMIX_E_INVALID, "input range [%lld, %lld) is not inside the track [0, %lld)", (long long)in_begin,
+                    (long long)(in_begin + in_len), (long long)n_total);
+    if (seg_begin < 0 || seg_end < seg_begin || seg_end > n_total)
+        return fail(UPMIX_E_INVALID, "segment [%lld, %lld) is not inside the track [0, %lld)", (long long)seg_begin,
+                    (long long)seg_end, (long long)n_total);
+    if (seg_end == seg_begin) return UPMIX_OK;
+    const int64_t need_lo = std::max<int64_t>(0, seg_begin - plan->halo), need_hi = std::min(n_total, seg_end + plan->halo);
+    if (in_begin > need_lo || in_begin + in_len < need_hi)
+        return fail(UPMIX_E_INVALID, "input range [%lld, %lld) does not cover the halo'd segment [%lld, %lld)", (long long)in_begin,
+                    (long long)(in_begin + in_len), (long long)need_lo, (long long)need_hi);
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return fail(UPMIX_E_CUDA, "cannot select device %d", plan->device);
+    return run_segment(plan, L, R, in_begin, in_begin + in_len, n_total, seg_begin, seg_end, n_tracks, in_stride, out_c, out_l,
+                       out_r, out_stride, workspace, workspace_bytes, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int upmix_process(const UpmixPlan* plan, const float* L, const float* R, int64_t n_samples, int n_tracks,
+                  int64_t in_stride, float* out_c, float* out_l, float* out_r, int64_t out_stride, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
+    if (n_samples == 0) return check_io(plan, L, R, out_c, out_l, out_r, n_tracks);
+    return upmix_process_segment(plan, L, R, 0, n_samples, n_samples, 0, n_samples, n_tracks, in_stride, out_c, out_l, out_r,
+                                 out_stride, workspace, workspace_bytes, stream);
+}
+
+// ---- block streaming ---------------------------------------------------------------------------
+// state layout (floats): [track][2][delay] input history, then per band [track][3][n_fft] rings.
+int64_t upmix_stream_delay(const UpmixPlan* plan) { return plan ? plan->halo : fail(UPMIX_E_INVALID, "plan is NULL"); }
+
+int64_t upmix_stream_state_bytes(const UpmixPlan* plan, int n_tracks) {
+    if (!plan || n_tracks < 1) return fail(UPMIX_E_INVALID, "bad plan / n_tracks");
+    int64_t floats = round_up(2 * plan->halo * n_tracks, 64);
+    for (const BandDev& b : plan->bands) floats += round_up(3LL * b.n_fft * n_tracks, 64);
+    return floats * (int64_t)sizeof(float);
+}
+
+int upmix_stream_reset(const UpmixPlan* plan, void* state, int n_tracks, void* stream) {
+    if (!plan || !state) return fail(UPMIX_E_INVALID, "plan / state is NULL");
+    DeviceGuard guard(plan->device);
+    CU_CHECK(cudaMemsetAsync(state, 0, (size_t)upmix_stream_state_bytes(plan, n_tracks), reinterpret_cast<cudaStream_t>(stream)));
+    return UPMIX_OK;
+}
+
+int64_t upmix_stream_workspace_bytes(const UpmixPlan* plan, int n_new, int n_tracks) {
+    if (!plan || n_new < 1 || n_tracks < 1) return fail(UPMIX_E_INVALID, "bad arguments");
+    const int64_t stage = round_up(2LL * n_tracks * (plan->halo + n_new) * (int64_t)sizeof(float), 256);
+    return stage + make_layout(plan, n_new, n_tracks).total;
+}
+
+int upmix_stream_block(const UpmixPlan* plan, void* state, int64_t samples_done, const float* in_l, const float* in_r,
+                       int n_new, int n_tracks, int64_t in_stride, float* out_c, float* out_l, float* out_r,
+                       int64_t out_stride, void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_io(plan, in_l, in_r, out_c, out_l, out_r, n_tracks);
+    if (rc) return rc;
+    if (!state) return fail(UPMIX_E_INVALID, "state is NULL");
+    if (n_new < 1 || samples_done < 0) return fail(UPMIX_E_INVALID, "bad n_new / samples_done");
+    for (const BandDev& b : plan->bands) {
+        if (b.n_fft > FUSED_MAX_N) return fail(UPMIX_E_UNSUPPORTED, "block streaming needs n_fft <= %d", FUSED_MAX_N);
+        if (n_new % b.hop != 0 || samples_done % b.hop != 0)
+            return fail(UPMIX_E_INVALID, "block of %d samples is not a multiple of hop %d", n_new, b.hop);
+    }
+    const int64_t need = upmix_stream_workspace_bytes(plan, n_new, n_tracks);
+    if (workspace_bytes < need) return fail(UPMIX_E_WORKSPACE, "workspace too small: %lld given, %lld needed", (long long)workspace_bytes, (long long)need);
+    DeviceGuard guard(plan->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t D = plan->halo;
+    const int64_t span = D + n_new;
+    float* hist = reinterpret_cast<float*>(state);
+    float* stage = reinterpret_cast<float*>(workspace);       // [2][track][span]
+    const int64_t stage_bytes = round_up(2LL * n_tracks * span * (int64_t)sizeof(float), 256);
+    // stage = history ++ new block (per channel, per track); history <- last D samples of stage
+    for (int ch = 0; ch < 2; ch++) {
+        const float* src = ch ? in_r : in_l;
+        float* dst = stage + (int64_t)ch * n_tracks * span;
+        CU_CHECK(cudaMemcpy2DAsync(dst, span * sizeof(float), hist + (int64_t)ch * n_tracks * D, D * sizeof(float),
+                                   D * sizeof(float), n_tracks, cudaMemcpyDeviceToDevice, st));
+        CU_CHECK(cudaMemcpy2DAsync(dst + D, span * sizeof(float), src, in_stride * sizeof(float), (size_t)n_new * sizeof(float),
+                                   n_tracks, cudaMemcpyDeviceToDevice, st));
+        CU_CHECK(cudaMemcpy2DAsync(hist + (int64_t)ch * n_tracks * D, D * sizeof(float), dst + n_new, span * sizeof(float),
+                                   D * sizeof(float), n_tracks, cudaMemcpyDeviceToDevice, st));
+    }
+    std::vector<float*> rings;
+    float* rp = hist + round_up(2 * D * n_tracks, 64);
+    for (const BandDev& b : plan->bands) {
+        rings.push_back(rp);
+        rp += round_up(3LL * b.n_fft * n_tracks, 64);
+    }
+    const int64_t seg_begin = samples_done - D, seg_end = samples_done + n_new - D;
+    return run_segment(plan, stage, stage + (int64_t)n_tracks * span, seg_begin, samples_done + n_new, INT64_MAX / 4, seg_begin,
+                       seg_end, n_tracks, span, out_c, out_l, out_r, out_stride, reinterpret_cast<char*>(workspace) + stage_bytes,
+                       workspace_bytes - stage_bytes, rings.data(), st);
+}
+
+int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, const float* blk_l, const float* blk_r,
+                     int n_tracks, int64_t in_stride, float* out_c, float* out_l, float* out_r, int64_t out_stride,
+                     void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_io(plan, blk_l, blk_r, out_c, out_l, out_r, n_tracks);
+    if (rc) return rc;
+    if (!ring) return fail(UPMIX_E_INVALID, "ring is NULL");
+    if (plan->bands.size() != 1) return fail(UPMIX_E_INVALID, "upmix_frame_step needs a single-band plan");
+    const BandDev& b = plan->bands[0];
+    if (b.n_fft > FUSED_MAX_N) return fail(UPMIX_E_UNSUPPORTED, "frame stepping needs n_fft <= %d", FUSED_MAX_N);
+    if (frame_index < 0) return fail(UPMIX_E_INVALID, "negative frame index");
+    DeviceGuard guard(plan->device);
+    float* rings[1] = {reinterpret_cast<float*>(ring)};
+    const int64_t s0 = frame_index * b.hop;
+    return run_segment(plan, blk_l, blk_r, s0, s0 + b.n_fft, INT64_MAX / 4, s0, s0 + b.hop, n_tracks, in_stride, out_c, out_l,
+                       out_r, out_stride, workspace, workspace_bytes, rings, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int upmix_process_host(const UpmixPlan* plan, const float* L, const float* R, int64_t n_samples, float* out_c,
+                       float* out_l, float* out_r) {
+    if (!plan) return fail(UPMIX_E_INVALID, "plan is NULL");
+    if (!L || !R || !out_l || !out_r || (plan->out_mode == UPMIX_OUT_LSCRS && !out_c)) return fail(UPMIX_E_INVALID, "NULL buffer");
+    if (n_samples <= 0) return n_samples == 0 ? UPMIX_OK : fail(UPMIX_E_INVALID, "negative length");
+    DeviceGuard guard(plan->device);
+    const int64_t nal = round_up(n_samples, 64);
+    const int64_t wsb = upmix_workspace_bytes(plan, n_samples, 1);
+    const int n_out = plan->out_mode == UPMIX_OUT_LSCRS ? 3 : 2;
+    float* dev = nullptr;
+    void* ws = nullptr;
+    cudaStream_t st = nullptr;
+    int rc = UPMIX_OK;
+    cudaError_t e = cudaMalloc(&dev, (size_t)(2 + n_out) * nal * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&ws, (size_t)wsb);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) rc = fail(UPMIX_E_CUDA, "allocation failed: %s", cudaGetErrorString(e));
+    if (rc == UPMIX_OK) {
+        float* dl = dev;
+        float* dr = dev + nal;
+        float* o0 = dev + 2 * nal;      // FOLD: out_l, out_r;  LSCRS: out_c, out_l, out_r
+        float* oc = n_out == 3 ? o0 : nullptr;
+        float* ol = n_out == 3 ? o0 + nal : o0;
+        float* orr = ol + nal;
+        e = cudaMemcpyAsync(dl, L, (size_t)n_samples * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dr, R, (size_t)n_samples * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) rc = fail(UPMIX_E_CUDA, "H2D failed: %s", cudaGetErrorString(e));
+        if (rc == UPMIX_OK) rc = upmix_process(plan, dl, dr, n_samples, 1, nal, oc, ol, orr, nal, ws, wsb, st);
+        if (rc == UPMIX_OK) {
+            if (oc) e = cudaMemcpyAsync(out_c, oc, (size_t)n_samples * sizeof(float), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out_l, ol, (size_t)n_samples * sizeof(float), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out_r, orr, (size_t)n_samples * sizeof(float), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) rc = fail(UPMIX_E_CUDA, "D2H / sync failed: %s", cudaGetErrorString(e));
+        }
+    }
+    if (st) cudaStreamDestroy(st);
+    cudaFree(ws);
+    cudaFree(dev);
+    return rc;
+}
+
+}  // extern "C"

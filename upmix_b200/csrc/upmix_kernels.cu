@@ -1,0 +1,502 @@
+// Hand-written sm_100a kernels for the multi-band STFT centre-extraction path.
+//
+//   band_fused_kernel<N>    N <= 8192: whole per-band chain in one CTA per run of hops --
+//                           frame load + analysis window -> packed complex FFT (L + iR) in shared
+//                           memory -> Hermitian split, band gain, centre mask -> inverse FFT of
+//                           Ls + i*Rs (N points) and of C (N/2 points, real-signal packing) ->
+//                           synthesis window -> overlap-add ring in shared memory -> finished hops.
+//   col_fwd_kernel          N >= 16384 (four-step, N = 16 x N2): radix-16 column DFT of the windowed
+//   row_mask_kernel<N2>     frame in registers; N2-point row FFT + mask + inverse row FFT in shared
+//   col_inv_ola_kernel      memory; radix-16 inverse column DFT + synthesis window + overlap-add in
+//                           registers.
+//   band_sum_kernel         sums the per-band outputs in band order (center_extraction.py:503-511)
+//                           and applies the output mode (Ls/C/Rs or L+0.5C / R+0.5C fold-down).
+//
+// Reference behaviour reproduced: center_extraction.py:353-472 (per-band chain), bela/upmix.cpp:238-306.
+#include "fft_device.cuh"
+#include "upmix_kernels.cuh"
+#include "upmix_launch.h"
+
+namespace upmix {
+
+// ---------------------------------------------------------------------------------------------
+// fused single-CTA band kernel
+// ---------------------------------------------------------------------------------------------
+template <int N>
+struct FusedCfg {
+    static constexpr int T = (N / 8 < 32) ? 32 : (N / 8 > 512 ? 512 : N / 8);
+    static constexpr int MINB = 512 / T;          // caps registers at 128 per thread
+    static constexpr int SMEM = (PADSZ(N) + PADSZ(N / 2)) * (int)sizeof(float2) + 3 * N * (int)sizeof(float);
+};
+
+template <int N>
+__global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_kernel(const BandDev b, const SegArgs a) {
+    constexpr int T = FusedCfg<N>::T;
+    constexpr int M = N / 2;
+    constexpr int TWS = TW_N / N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Z = reinterpret_cast<float2*>(smem_raw);
+    float2* Cz = Z + PADSZ(N);
+    float* ring = reinterpret_cast<float*>(Cz + PADSZ(M));   // [3][N]: C, Ls, Rs
+
+    const int tid = threadIdx.x;
+    const int H = b.hop;
+    const int K = N / H;
+    const long long h0 = a.hop_begin + (long long)blockIdx.x * a.hops_per_run;
+    const long long h1 = min(h0 + (long long)a.hops_per_run, a.hop_end);
+    if (h0 >= h1) return;
+    const int track = blockIdx.y;
+    const float* __restrict__ inl = a.in_l + (long long)track * a.in_stride;
+    const float* __restrict__ inr = a.in_r + (long long)track * a.in_stride;
+    float* outp[3] = {a.out_c + (long long)track * a.out_stride, a.out_l + (long long)track * a.out_stride,
+                      a.out_r + (long long)track * a.out_stride};
+    float* st_ring = a.state ? a.state + (long long)track * 3 * N : nullptr;
+
+    long long f_begin;
+    if (st_ring) {
+        f_begin = h0;
+        const int nb0 = (int)(h0 % K) * H;          // slot 0 of the saved ring = first sample of frame h0
+        for (int i = tid; i < 3 * N; i += T) {
+            const int ch = i / N, n = i - ch * N;
+            ring[ch * N + ((nb0 + n) & (N - 1))] = st_ring[i];
+        }
+    } else {
+        f_begin = max(0LL, h0 - (K - 1));
+        for (int i = tid; i < 3 * N; i += T) ring[i] = 0.f;
+    }
+    __syncthreads();
+
+    const float* __restrict__ ana = b.ana;
+    const float* __restrict__ syn = b.syn;
+    const float* __restrict__ gain = b.gain;
+    const float2* __restrict__ tw = b.tw;
+
+    for (long long f = f_begin; f < h1; ++f) {
+        const long long s0 = f * H;
+        const int base = (int)(f % K) * H;
+
+        // ---- forward: Z = FFT_N( ana * (L + iR) ) -----------------------------------------------
+        auto ld_in = [&](int, int n) -> float2 {
+            const long long s = s0 + n;
+            if (s >= a.in_begin && s < a.in_end) {
+                const float w = __ldg(ana + n);
+                return make_float2(__ldg(inl + (s - a.in_begin)) * w, __ldg(inr + (s - a.in_begin)) * w);
+            }
+            return make_float2(0.f, 0.f);
+        };
+        auto st_z = [&](int, int k, float2 v) { Z[PAD(k)] = v; };
+        fft_smem<N, -1, T, 1, false>(Z, tid, tw, TWS, ld_in, st_z);
+
+        // ---- split / gain / mask; Y1 = Ls + i*Rs in place, C packed for the half-size inverse ---
+        for (int k = tid; k <= M / 2; k += T) {
+            const int k2 = M - k;
+            const int km = (N - k) & (N - 1);
+            const float2 a1 = Z[PAD(k)], b1 = Z[PAD(km)];
+            const float2 a2 = Z[PAD(k2)], b2 = Z[PAD(M + k)];
+            const float g1 = __ldg(gain + k), g2 = __ldg(gain + k2);
+            float2 c1 = make_float2(0.f, 0.f), l1 = c1, r1 = c1, c2 = c1, l2 = c1, r2 = c1;
+            if (g1 != 0.f) split_gain_mask(a1, b1, g1, c1, l1, r1);
+            if (g2 != 0.f) split_gain_mask(a2, b2, g2, c2, l2, r2);
+            Z[PAD(k)] = make_float2(l1.x - r1.y, l1.y + r1.x);
+            Z[PAD(km)] = make_float2(l1.x + r1.y, r1.x - l1.y);
+            Z[PAD(k2)] = make_float2(l2.x - r2.y, l2.y + r2.x);
+            Z[PAD(M + k)] = make_float2(l2.x + r2.y, r2.x - l2.y);
+            // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);  IFFT_M(z)[m] = c[2m] + i c[2m+1]
+            const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
+            const float2 B = make_float2(c1.x - c2.x, c1.y + c2.y);
+            const float2 w = __ldg(tw + k * TWS);
+            const float2 D = cmul(B, make_float2(w.x, -w.y));
+            Cz[PAD(k)] = make_float2(A.x - D.y, A.y + D.x);
+            if (k > 0) Cz[PAD(M - k)] = make_float2(A.x + D.y, D.x - A.y);
+        }
+        __syncthreads();
+
+        // ---- inverse transforms, synthesis window, overlap-add (oldest frame first) --------------
+        auto ld_z = [&](int, int n) -> float2 { return Z[PAD(n)]; };
+        auto st_lr = [&](int, int n, float2 v) {
+            const float w = __ldg(syn + n);
+            const int p = (base + n) & (N - 1);
+            ring[N + p] += v.x * w;
+            ring[2 * N + p] += v.y * w;
+        };
+        fft_smem<N, +1, T, 1, true>(Z, tid, tw, TWS, ld_z, st_lr);
+        auto ld_c = [&](int, int n) -> float2 { return Cz[PAD(n)]; };
+        auto st_c = [&](int, int m, float2 v) {
+            const int n = 2 * m;
+            const int p = (base + n) & (N - 1);
+            ring[p] += v.x * __ldg(syn + n);
+            ring[p + 1] += v.y * __ldg(syn + n + 1);
+        };
+        fft_smem<M, +1, T, 1, true>(Cz, tid, tw, 2 * TWS, ld_c, st_c);
+
+        // ---- emit the hop this frame finished, clear its ring slots --------------------------------
+        const bool emit = f >= h0;
+        for (int i = tid; i < H; i += T) {
+            const long long s = s0 + i;
+            const bool wr = emit && s >= a.seg_begin && s < a.seg_end;
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                const float v = ring[ch * N + base + i];
+                ring[ch * N + base + i] = 0.f;
+                if (wr) outp[ch][s - a.out_begin] = v;
+            }
+        }
+        __syncthreads();
+    }
+    if (st_ring) {
+        // re-base the ring so that slot 0 is the first unfinished sample (frame h1 starts there)
+        const int nb = (int)(h1 % K) * H;
+        for (int i = tid; i < 3 * N; i += T) {
+            const int ch = i / N, n = i - ch * N;
+            st_ring[i] = ring[ch * N + ((nb + n) & (N - 1))];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// large-N path, N = 16 * N2
+// ---------------------------------------------------------------------------------------------
+// K1: one thread per (frame, column n2): windowed samples x[16 rows][n2] -> radix-16 DFT over the
+// rows -> twiddle W_N^{n2*k1} -> A[frame][k1][n2].
+__global__ void __launch_bounds__(128) col_fwd_kernel(const BandDev b, const SegArgs a, const WaveArgs w) {
+    const int N2 = b.n_fft / COL_R;
+    const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int fl = blockIdx.y;
+    const int track = blockIdx.z;
+    if (n2 >= N2) return;
+    const long long f = w.frame0 + fl;
+    const long long s0 = f * b.hop;
+    const float* __restrict__ inl = a.in_l + (long long)track * a.in_stride;
+    const float* __restrict__ inr = a.in_r + (long long)track * a.in_stride;
+    float2 v[COL_R];
+#pragma unroll
+    for (int r = 0; r < COL_R; r++) {
+        const int n = r * N2 + n2;
+        const long long s = s0 + n;
+        if (s >= a.in_begin && s < a.in_end) {
+            const float wn = __ldg(b.ana + n);
+            v[r] = make_float2(__ldg(inl + (s - a.in_begin)) * wn, __ldg(inr + (s - a.in_begin)) * wn);
+        } else {
+            v[r] = make_float2(0.f, 0.f);
+        }
+    }
+    Dft<COL_R, -1>::run(v);
+    float2* dst = w.a + (((long long)track * w.n_frames + fl) * COL_R) * N2 + n2;
+    dst[0] = v[0];
+#pragma unroll
+    for (int k1 = 1; k1 < COL_R; k1++) dst[(long long)k1 * N2] = cmul(v[k1], __ldg(b.tw_col + k1 * N2 + n2));
+}
+
+template <int N2>
+struct RowCfg {
+    static constexpr int T = (N2 / 4 > 512) ? 512 : N2 / 4;
+    static constexpr int SMEM = 6 * PADSZ(N2) * (int)sizeof(float2);
+};
+
+// K2: one CTA per (row pair, frame pair, track).  Rows k1 and 16-k1 of the frame's spectrum are
+// mirror images of each other (bin k <-> N-k), so the CTA holds both rows of both frames, finishes
+// the forward transform along the rows, applies split/gain/mask, and starts the inverse transform
+// (rows) of Ls+iRs for each frame and of C(even frame) + i*C(odd frame).
+template <int N2>
+__global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b, const WaveArgs w) {
+    constexpr int T = RowCfg<N2>::T;
+    constexpr int TWS = TW_N / N2;
+    constexpr int RS = PADSZ(N2);
+    constexpr int N = COL_R * N2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* S = reinterpret_cast<float2*>(smem_raw);   // 6 rows: f0a f0b f1a f1b ca cb
+    const int tid = threadIdx.x;
+    const int pr = blockIdx.x;                          // 0: rows (0, 8) self-mirrored; p: rows (p, 16-p)
+    const int fp = blockIdx.y;
+    const int track = blockIdx.z;
+    const int ka = pr, kb = pr == 0 ? COL_R / 2 : COL_R - pr;
+    const long long fbase = ((long long)track * w.n_frames + 2 * fp) * COL_R;
+    const float2* __restrict__ A = w.a;
+    const float2* __restrict__ tw = b.tw;
+    const float* __restrict__ gain = b.gain;
+
+    // forward row transforms: rows (f0,ka) (f0,kb) then (f1,ka) (f1,kb)
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+        auto ld = [&](int row, int n) -> float2 {
+            const int k1 = row ? kb : ka;
+            return A[(fbase + (long long)g * COL_R + k1) * N2 + n];
+        };
+        float2* buf = S + 2 * g * RS;
+        auto st = [&](int row, int k, float2 v) { buf[row * RS + PAD(k)] = v; };
+        fft_smem<N2, -1, T, 2, false>(buf, tid, tw, TWS, ld, st);
+    }
+
+    // split / gain / mask over mirror pairs
+    const int n_items = pr == 0 ? N2 + 1 : N2;
+    for (int it = tid; it < n_items; it += T) {
+        int lo_row, lo_idx, hi_row, hi_idx, bin;
+        if (pr != 0) {
+            const int k2 = it;
+            if (k2 < N2 / 2) { lo_row = 0; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = ka + COL_R * k2; }
+            else { lo_row = 1; lo_idx = N2 - 1 - k2; hi_row = 0; hi_idx = k2; bin = kb + COL_R * (N2 - 1 - k2); }
+        } else if (it <= N2 / 2) {          // row 0: bin 16*k2 <-> 16*(N2-k2)
+            lo_row = 0; lo_idx = it; hi_row = 0; hi_idx = (N2 - it) & (N2 - 1); bin = COL_R * it;
+        } else {                            // row 8: bin 8+16*k2 <-> 8+16*(N2-1-k2)
+            const int k2 = it - (N2 / 2 + 1);
+            lo_row = 1; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = COL_R / 2 + COL_R * k2;
+        }
+        const int lo = lo_row * RS + PAD(lo_idx), hi = hi_row * RS + PAD(hi_idx);
+        const float g = __ldg(gain + bin);
+        float2 c[2];
+#pragma unroll
+        for (int fr = 0; fr < 2; fr++) {
+            float2* buf = S + 2 * fr * RS;
+            float2 ls = make_float2(0.f, 0.f), rs = ls;
+            c[fr] = ls;
+            if (g != 0.f) split_gain_mask(buf[lo], buf[hi], g, c[fr], ls, rs);
+            buf[lo] = make_float2(ls.x - rs.y, ls.y + rs.x);
+            buf[hi] = make_float2(ls.x + rs.y, rs.x - ls.y);
+        }
+        float2* cb = S + 4 * RS;
+        cb[lo] = make_float2(c[0].x - c[1].y, c[0].y + c[1].x);
+        cb[hi] = make_float2(c[0].x + c[1].y, c[1].x - c[0].y);
+    }
+    __syncthreads();
+
+    // inverse row transforms, results to the wave scratch
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+        float2* buf = S + 2 * g * RS;
+        auto ld = [&](int row, int n) -> float2 { return buf[row * RS + PAD(n)]; };
+        float2* dst = g < 2 ? w.b1 + (fbase + (long long)g * COL_R) * N2
+                            : w.b2 + (((long long)track * (w.n_frames / 2) + fp) * COL_R) * N2;
+        auto st = [&](int row, int n, float2 v) {
+            const int k1 = row ? kb : ka;
+            dst[(long long)k1 * N2 + n] = v;
+        };
+        fft_smem<N2, +1, T, 2, true>(buf, tid, tw, TWS, ld, st);
+    }
+    (void)N;
+}
+
+// K3: one thread per (column n2, run of hops, track).  For every frame pair of the run (plus the
+// frames before it whose tails reach into the run) the thread finishes the inverse transform down
+// its column (radix-16), applies the synthesis window and overlap-adds in registers: a frame shifts
+// the 16-row accumulator by 4 rows (hop = N/4 = 4*N2), the 4 rows that fall out are finished samples.
+__global__ void __launch_bounds__(128) col_inv_ola_kernel(const BandDev b, const SegArgs a, const WaveArgs w) {
+    const int N2 = b.n_fft / COL_R;
+    const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n2 >= N2) return;
+    const int track = blockIdx.z;
+    const int H = b.hop;
+    const long long h0 = a.hop_begin + (long long)blockIdx.y * a.hops_per_run;
+    const long long h1 = min(h0 + (long long)a.hops_per_run, a.hop_end);
+    if (h0 >= h1) return;
+    const long long f_begin = max(0LL, h0 - 3);
+    float* outp[3] = {a.out_c + (long long)track * a.out_stride, a.out_l + (long long)track * a.out_stride,
+                      a.out_r + (long long)track * a.out_stride};
+    const float* __restrict__ syn = b.syn;
+    const float2* __restrict__ twc = b.tw_col;
+
+    float acc[3][COL_R];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++)
+#pragma unroll
+        for (int i = 0; i < COL_R; i++) acc[ch][i] = 0.f;
+
+    for (long long p = f_begin >> 1; 2 * p < h1; ++p) {
+        const long long fl = 2 * p - w.frame0;              // local index of the even frame
+        const float2* __restrict__ B2 = w.b2 + (((long long)track * (w.n_frames / 2) + (fl >> 1)) * COL_R) * N2 + n2;
+        float2 cc[COL_R];
+        cc[0] = B2[0];
+#pragma unroll
+        for (int k1 = 1; k1 < COL_R; k1++) {
+            const float2 t = __ldg(twc + k1 * N2 + n2);
+            cc[k1] = cmul(B2[(long long)k1 * N2], make_float2(t.x, -t.y));
+        }
+        Dft<COL_R, +1>::run(cc);                            // cc[n1] = (c_even[n], c_odd[n]), n = n1*N2 + n2
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const long long f = 2 * p + half;
+            const float2* __restrict__ B1 = w.b1 + (((long long)track * w.n_frames + fl + half) * COL_R) * N2 + n2;
+            float2 v[COL_R];
+            v[0] = B1[0];
+#pragma unroll
+            for (int k1 = 1; k1 < COL_R; k1++) {
+                const float2 t = __ldg(twc + k1 * N2 + n2);
+                v[k1] = cmul(B1[(long long)k1 * N2], make_float2(t.x, -t.y));
+            }
+            Dft<COL_R, +1>::run(v);
+#pragma unroll
+            for (int n1 = 0; n1 < COL_R; n1++) {
+                const float wn = __ldg(syn + n1 * N2 + n2);
+                acc[0][n1] += (half ? cc[n1].y : cc[n1].x) * wn;
+                acc[1][n1] += v[n1].x * wn;
+                acc[2][n1] += v[n1].y * wn;
+            }
+            const bool emit = f >= h0 && f < h1;
+#pragma unroll
+            for (int n1 = 0; n1 < COL_R / 4; n1++) {
+                const long long s = f * H + n1 * N2 + n2;
+                if (emit && s >= a.seg_begin && s < a.seg_end) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) outp[ch][s - a.out_begin] = acc[ch][n1];
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+#pragma unroll
+                for (int i = 0; i < COL_R - COL_R / 4; i++) acc[ch][i] = acc[ch][i + COL_R / 4];
+#pragma unroll
+                for (int i = COL_R - COL_R / 4; i < COL_R; i++) acc[ch][i] = 0.f;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// band summation + output mode
+// ---------------------------------------------------------------------------------------------
+// ws layout: [band][channel C,Ls,Rs][track][ws_seg] (ws_seg >= seg_len, multiple of 4).  Bands are added in list order, in float32, as
+// center_extraction.py:503-511 does.  mode 0: C, Ls, Rs.  mode 1 (fold-down, bela/upmix.cpp:295-303,
+// 487-490): out_l = sum_b (Ls_b + 0.5 C_b), out_r = sum_b (Rs_b + 0.5 C_b); out_c untouched.
+template <int VEC>
+__global__ void __launch_bounds__(256) band_sum_kernel(const float* __restrict__ ws, int n_bands, int n_tracks,
+                                                       long long seg_len, long long ws_seg,
+                                                       float* __restrict__ out_c,
+                                                       float* __restrict__ out_l, float* __restrict__ out_r,
+                                                       long long out_stride, int mode) {
+    const int track = blockIdx.y;
+    const long long band_stride = 3LL * n_tracks * ws_seg;
+    const long long ch_stride = (long long)n_tracks * ws_seg;
+    const long long nvec = seg_len / VEC;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+         i += (long long)gridDim.x * blockDim.x) {
+        float c[VEC], l[VEC], r[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; j++) c[j] = l[j] = r[j] = 0.f;
+        for (int bnd = 0; bnd < n_bands; bnd++) {
+            const float* p = ws + bnd * band_stride + track * ws_seg + i * VEC;
+            float vc[VEC], vl[VEC], vr[VEC];
+            if (VEC == 4) {
+                *reinterpret_cast<float4*>(vc) = __ldcs(reinterpret_cast<const float4*>(p));
+                *reinterpret_cast<float4*>(vl) = __ldcs(reinterpret_cast<const float4*>(p + ch_stride));
+                *reinterpret_cast<float4*>(vr) = __ldcs(reinterpret_cast<const float4*>(p + 2 * ch_stride));
+            } else {
+                vc[0] = p[0]; vl[0] = p[ch_stride]; vr[0] = p[2 * ch_stride];
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; j++) {
+                if (mode == 0) { c[j] += vc[j]; l[j] += vl[j]; r[j] += vr[j]; }
+                else { l[j] += vl[j] + 0.5f * vc[j]; r[j] += vr[j] + 0.5f * vc[j]; }
+            }
+        }
+        const long long o = track * out_stride + i * VEC;
+        if (VEC == 4) {
+            if (mode == 0) __stcs(reinterpret_cast<float4*>(out_c + o), *reinterpret_cast<float4*>(c));
+            __stcs(reinterpret_cast<float4*>(out_l + o), *reinterpret_cast<float4*>(l));
+            __stcs(reinterpret_cast<float4*>(out_r + o), *reinterpret_cast<float4*>(r));
+        } else {
+            if (mode == 0) out_c[o] = c[0];
+            out_l[o] = l[0];
+            out_r[o] = r[0];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers (called from upmix_capi.cu)
+// ---------------------------------------------------------------------------------------------
+template <int N>
+static cudaError_t launch_fused_n(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st) {
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(band_fused_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             FusedCfg<N>::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done[dev & 63] = true;
+    }
+    band_fused_kernel<N><<<dim3(n_runs, n_tracks), FusedCfg<N>::T, FusedCfg<N>::SMEM, st>>>(b, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_band_fused(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st) {
+    switch (b.n_fft) {
+        case 64: return launch_fused_n<64>(b, a, n_runs, n_tracks, st);
+        case 128: return launch_fused_n<128>(b, a, n_runs, n_tracks, st);
+        case 256: return launch_fused_n<256>(b, a, n_runs, n_tracks, st);
+        case 512: return launch_fused_n<512>(b, a, n_runs, n_tracks, st);
+        case 1024: return launch_fused_n<1024>(b, a, n_runs, n_tracks, st);
+        case 2048: return launch_fused_n<2048>(b, a, n_runs, n_tracks, st);
+        case 4096: return launch_fused_n<4096>(b, a, n_runs, n_tracks, st);
+        case 8192: return launch_fused_n<8192>(b, a, n_runs, n_tracks, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+int fused_smem_bytes(int n_fft) {
+    switch (n_fft) {
+        case 64: return FusedCfg<64>::SMEM;
+        case 128: return FusedCfg<128>::SMEM;
+        case 256: return FusedCfg<256>::SMEM;
+        case 512: return FusedCfg<512>::SMEM;
+        case 1024: return FusedCfg<1024>::SMEM;
+        case 2048: return FusedCfg<2048>::SMEM;
+        case 4096: return FusedCfg<4096>::SMEM;
+        case 8192: return FusedCfg<8192>::SMEM;
+        default: return -1;
+    }
+}
+
+cudaError_t launch_col_fwd(const BandDev& b, const SegArgs& a, const WaveArgs& w, int n_tracks, cudaStream_t st) {
+    const int n2 = b.n_fft / COL_R;
+    col_fwd_kernel<<<dim3((n2 + 127) / 128, w.n_frames, n_tracks), 128, 0, st>>>(b, a, w);
+    return cudaGetLastError();
+}
+
+template <int N2>
+static cudaError_t launch_row_n(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(row_mask_kernel<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             RowCfg<N2>::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done[dev & 63] = true;
+    }
+    row_mask_kernel<N2><<<dim3(COL_R / 2, w.n_frames / 2, n_tracks), RowCfg<N2>::T, RowCfg<N2>::SMEM, st>>>(b, w);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_row_mask(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
+    switch (b.n_fft / COL_R) {
+        case 1024: return launch_row_n<1024>(b, w, n_tracks, st);
+        case 2048: return launch_row_n<2048>(b, w, n_tracks, st);
+        case 4096: return launch_row_n<4096>(b, w, n_tracks, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_col_inv_ola(const BandDev& b, const SegArgs& a, const WaveArgs& w, int n_runs, int n_tracks,
+                               cudaStream_t st) {
+    const int n2 = b.n_fft / COL_R;
+    col_inv_ola_kernel<<<dim3((n2 + 127) / 128, n_runs, n_tracks), 128, 0, st>>>(b, a, w);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_band_sum(const float* ws, int n_bands, int n_tracks, long long seg_len, long long ws_seg,
+                            float* out_c, float* out_l, float* out_r, long long out_stride, int mode,
+                            cudaStream_t st) {
+    if (seg_len <= 0) return cudaSuccess;
+    const bool vec = (seg_len % 4 == 0) && (ws_seg % 4 == 0) && (out_stride % 4 == 0 || n_tracks == 1) &&
+                     ((reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(out_l) |
+                       reinterpret_cast<uintptr_t>(out_r) | (mode == 0 ? reinterpret_cast<uintptr_t>(out_c) : 0)) % 16 == 0);
+    const long long nvec = vec ? seg_len / 4 : seg_len;
+    long long blocks = (nvec + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    dim3 grid((unsigned)blocks, n_tracks);
+    if (vec) band_sum_kernel<4><<<grid, 256, 0, st>>>(ws, n_bands, n_tracks, seg_len, ws_seg, out_c, out_l, out_r, out_stride, mode);
+    else band_sum_kernel<1><<<grid, 256, 0, st>>>(ws, n_bands, n_tracks, seg_len, ws_seg, out_c, out_l, out_r, out_stride, mode);
+    return cudaGetLastError();
+}
+
+}  // namespace upmix

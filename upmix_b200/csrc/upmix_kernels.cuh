@@ -1,0 +1,58 @@
+// Kernel-side argument blocks shared by the kernels (upmix_kernels.cu) and the C-ABI host code
+// (upmix_capi.cu).  Vocabulary follows the reference: a *band* is one crossover interval with its
+// own STFT size (center_extraction.py:518-580), a *frame* is one STFT block starting at f*hop
+// (center_extraction.py:448-460), a *hop* is the run of `hop` output samples that frame f finishes
+// (center_extraction.py:396-399), a *track* is one stereo signal.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace upmix {
+
+constexpr int TW_N = 8192;        // master twiddle table: tw[m] = exp(-2*pi*i*m/TW_N)
+constexpr int COL_R = 16;         // column radix of the large-N (four-step) path
+constexpr int FUSED_MAX_N = 8192; // largest STFT size handled by the single-CTA fused kernel
+constexpr int LARGE_MAX_N = 65536;
+
+// Device tables of one band (all in global memory, read-only during processing).
+struct BandDev {
+    int n_fft;
+    int hop;
+    const float* ana;          // [n_fft]       analysis window
+    const float* syn;          // [n_fft]       synthesis window / n_fft (the inverse FFT is unnormalised)
+    const float* gain;         // [n_fft/2+1]   band-limit gain
+    const float2* tw;          // [TW_N]        master twiddles
+    const float2* tw_col;      // [16][n_fft/16] exp(-2*pi*i*k1*n2/n_fft), large path only
+};
+
+// Where the samples are.  Global sample index s of a track lives at in[s - in_begin] for
+// in_begin <= s < in_end; everything else reads as zero (signal start, zero-extended tail, or the
+// part of the track another shard owns).  Output sample s goes to out[ch][s - out_begin] when
+// seg_begin <= s < seg_end.
+struct SegArgs {
+    const float* in_l;
+    const float* in_r;
+    long long in_stride;       // elements between tracks
+    long long in_begin, in_end;
+    float* out_c;
+    float* out_l;
+    float* out_r;
+    long long out_stride;      // elements between tracks
+    long long out_begin;
+    long long seg_begin, seg_end;
+    long long hop_begin, hop_end;   // global hop indices to produce
+    int hops_per_run;               // hops handled by one CTA / thread run (plus warm-up frames)
+    float* state;                   // optional streaming state [track][3][n_fft]: ring carried between calls
+};
+
+// Scratch of one wave of the large-N path.  Frames [frame0, frame0 + n_frames) of every track,
+// frame0 even, n_frames even.
+struct WaveArgs {
+    float2* a;        // [track][n_frames][16][n2]   column-transformed, twiddled input spectra
+    float2* b1;       // [track][n_frames][16][n2]   row-inverse-transformed Ls + i*Rs
+    float2* b2;       // [track][n_frames/2][16][n2] row-inverse-transformed C(f even) + i*C(f odd)
+    long long frame0;
+    int n_frames;
+};
+
+}  // namespace upmix

@@ -1,0 +1,18 @@
+// Launch entry points implemented in upmix_kernels.cu, called by the C-ABI layer (upmix_capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "upmix_kernels.cuh"
+
+namespace upmix {
+
+cudaError_t launch_band_fused(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st);
+int fused_smem_bytes(int n_fft);
+cudaError_t launch_col_fwd(const BandDev& b, const SegArgs& a, const WaveArgs& w, int n_tracks, cudaStream_t st);
+cudaError_t launch_row_mask(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st);
+cudaError_t launch_col_inv_ola(const BandDev& b, const SegArgs& a, const WaveArgs& w, int n_runs, int n_tracks,
+                               cudaStream_t st);
+cudaError_t launch_band_sum(const float* ws, int n_bands, int n_tracks, long long seg_len, long long ws_seg,
+                            float* out_c, float* out_l, float* out_r, long long out_stride, int mode,
+                            cudaStream_t st);
+
+}  // namespace upmix
