@@ -81,15 +81,16 @@ int upmix_process(const UpmixPlan* plan, const float* L, const float* R, int64_t
 
 /* One time shard.  The track has n_total samples; L/R hold its samples [in_begin, in_begin+in_len)
  * (index 0 = sample in_begin); outputs receive samples [seg_begin, seg_end) (index 0 = seg_begin).
- * The input range must cover [seg_begin - (n_fft-hop), seg_end + (n_fft-hop)) clipped to the track
- * for the plan's largest band; frames keep their global index, so the result is bit-identical to
- * the same samples of an unsharded run. */
+ * The input range must cover [seg_begin - halo, seg_end + halo) clipped to the track, halo =
+ * upmix_segment_halo(plan); frames keep their global index, so the result is bit-identical to the
+ * same samples of an unsharded run. */
 int upmix_process_segment(const UpmixPlan* plan, const float* L, const float* R, int64_t in_begin, int64_t in_len,
                           int64_t n_total, int64_t seg_begin, int64_t seg_end, int n_tracks, int64_t in_stride,
                           float* out_c, float* out_l, float* out_r, int64_t out_stride, void* workspace,
                           int64_t workspace_bytes, void* stream);
 
-/* Input margin (samples each side) upmix_process_segment needs: max over bands of n_fft - hop. */
+/* Input margin (samples each side) upmix_process_segment needs: max over bands of n_fft - hop, or of
+ * n_fft for bands above 8192 (their frames are transformed in even/odd pairs). */
 int64_t upmix_segment_halo(const UpmixPlan* plan);
 
 /* Block streaming (bands with n_fft <= 8192).  `state` is caller-owned device memory of
@@ -123,6 +124,11 @@ int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, con
  * device-pointer entry points. */
 int upmix_process_host(const UpmixPlan* plan, const float* L, const float* R, int64_t n_samples, float* out_c,
                        float* out_l, float* out_r);
+
+/* Measurement helpers (bench.py): number of kernels this library launched since the last reset, and
+ * the FP32 FMA throughput of the device (the roofline denominator of this FP32-bound path). */
+int64_t upmix_debug_launch_count(int reset);
+int upmix_measure_fp32_tflops(int device, double* tflops, int* sm_count);
 
 #ifdef __cplusplus
 }

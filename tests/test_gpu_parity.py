@@ -201,7 +201,8 @@ def test_known_answers_on_device(ce):
     assert float(l.abs().max()) < 1e-5 and float(r.abs().max()) < 1e-5 and float(c.abs().max()) > 0.05
     # hard-panned: no centre, no right
     c, l, r = ce.extract_center_left_right_multi_band_in_memory(dl, torch.zeros_like(dl), sr, ext)
-    assert float(c.abs().max()) == 0.0 and float(r.abs().max()) == 0.0 and float(l.abs().max()) > 0.05
+    # (float32: L + i*0 through a complex FFT leaves ~1e-8 of leakage in the split, not exact zeros)
+    assert float(c.abs().max()) < 1e-6 and float(r.abs().max()) < 1e-6 and float(l.abs().max()) > 0.05
     # Ls + C does not depend on the other channel (per-frame linearity)
     c1, l1, _ = ce.extract_center_left_right_multi_band_in_memory(dl, dr, sr, ext)
     c2, l2, _ = ce.extract_center_left_right_multi_band_in_memory(dl, (dr * 0.3).flip(0).contiguous(), sr, ext)

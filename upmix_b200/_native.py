@@ -68,6 +68,8 @@ def load_library():
     _sig(lib.upmix_stream_block, i32, [vp, vp, i64, vp, vp, i32, i32, i64, vp, vp, vp, i64, vp, i64, vp])
     _sig(lib.upmix_process_host, i32, [vp, vp, vp, i64, vp, vp, vp])
     _sig(lib.upmix_frame_step, i32, [vp, vp, i64, vp, vp, i32, i64, vp, vp, vp, i64, vp, i64, vp])
+    _sig(lib.upmix_debug_launch_count, i64, [i32])
+    _sig(lib.upmix_measure_fp32_tflops, i32, [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)])
     _lib = lib
     return lib
 
@@ -76,7 +78,20 @@ EXPORTS = ("upmix_last_error", "upmix_version", "upmix_plan_create", "upmix_plan
            "upmix_plan_n_bands", "upmix_workspace_bytes", "upmix_segment_halo", "upmix_process",
            "upmix_process_segment", "upmix_stream_state_bytes", "upmix_stream_workspace_bytes",
            "upmix_stream_delay", "upmix_stream_reset", "upmix_stream_block", "upmix_process_host",
-           "upmix_frame_step")
+           "upmix_frame_step", "upmix_debug_launch_count", "upmix_measure_fp32_tflops")
+
+
+def launch_count(reset: bool = False) -> int:
+    """Kernels launched by the library since the last reset."""
+    return int(load_library().upmix_debug_launch_count(1 if reset else 0))
+
+
+def measure_fp32_tflops(device: int = 0):
+    """(TFLOP/s, SM count) of a pure FMA kernel on `device`."""
+    _torch()
+    v, n = ctypes.c_double(), ctypes.c_int()
+    _check(load_library().upmix_measure_fp32_tflops(int(device), ctypes.byref(v), ctypes.byref(n)))
+    return float(v.value), int(n.value)
 
 
 def _check(rc: int):
@@ -201,6 +216,30 @@ class Plan:
     # -- block streaming -------------------------------------------------------------------------
     def stream_open(self, n_tracks: int = 1):
         return Stream(self, n_tracks)
+
+    # -- host tensors (pinned staging) -------------------------------------------------------------
+    def process_host_tensors(self, L, R):
+        """L, R: float32 CPU torch tensors [n] (pinned memory makes the copies asynchronous).  Copies
+        them to the device, processes, copies the outputs into (cached) pinned host tensors and
+        waits.  Returns CPU tensors; they are overwritten by the next call on this plan."""
+        torch = _torch()
+        if L.dtype != torch.float32 or R.dtype != torch.float32 or L.dim() != 1 or L.shape != R.shape:
+            raise TypeError("L and R must be 1-D float32 CPU tensors of equal length")
+        n = L.shape[0]
+        n_out = 3 if self.out_mode == OUT_LSCRS else 2
+        dev = torch.device(f"cuda:{self.device}")
+        cache = getattr(self, "_host_cache", None)
+        if cache is None or cache[0] != n:
+            self._host_cache = cache = (n, torch.empty((2, n), dtype=torch.float32, device=dev),
+                                        torch.empty((n_out, 1, n), dtype=torch.float32, device=dev),
+                                        torch.empty((n_out, n), dtype=torch.float32, pin_memory=True))
+        _, d_in, d_out, h_out = cache
+        d_in[0].copy_(L, non_blocking=True)
+        d_in[1].copy_(R, non_blocking=True)
+        self.process_segment(d_in[0:1], d_in[1:2], 0, n, 0, n, out=d_out)
+        h_out.copy_(d_out[:, 0], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return tuple(h_out[i] for i in range(n_out))
 
     # -- host buffers ----------------------------------------------------------------------------
     def process_host(self, L: np.ndarray, R: np.ndarray):

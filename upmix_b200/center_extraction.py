@@ -343,6 +343,8 @@ def _run_plan(plan: "_native.Plan", L, R) -> tuple:
     torch = _native._torch()
     if _is_cuda_tensor(L):
         return plan.process(L, R)
+    if isinstance(L, torch.Tensor):                 # host tensors (pinned): staged copies, tensors back
+        return plan.process_host_tensors(L.to(torch.float32), R.to(torch.float32))
     Lh, Rh = _as_host_f32(L), _as_host_f32(R)
     if Lh.ndim != 1 or Lh.shape != Rh.shape:
         raise ValueError("L and R must be 1-D signals of equal length")
@@ -363,7 +365,8 @@ def extract_center_left_right_multi_band_in_memory(L, R, sr: float,
                                                    band_extractors: List[MultiBandExtractorAccu]) -> tuple:
     """All bands over the whole signal, summed in list order.  Returns (centre, left, right), float32,
     len(L) samples each.  numpy in -> numpy out; float32 CUDA tensors in ([n] or [tracks, n]) ->
-    CUDA tensors out, left on the device."""
+    CUDA tensors out, left on the device; CPU torch tensors in (pinned for asynchronous copies) ->
+    pinned CPU tensors out."""
     plan = plan_for(band_extractors, _native.OUT_LSCRS)
     return _run_plan(plan, L, R)
 

@@ -61,7 +61,8 @@ struct UpmixPlan {
     std::vector<BandDev> bands;
     void* tables = nullptr;     // one device allocation holding every table
     int max_large_n = 0;        // largest n_fft handled by the four-step path (0: none)
-    int64_t halo = 0;           // max over bands of n_fft - hop
+    int64_t halo = 0;           // input margin a time shard needs on each side
+    int64_t delay = 0;          // max over bands of n_fft - hop (block streaming latency)
     int sm_count = 148;
 };
 
@@ -277,7 +278,10 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
             off += 2LL * d.n_fft;
             p->max_large_n = std::max(p->max_large_n, d.n_fft);
         }
-        p->halo = std::max<int64_t>(p->halo, d.n_fft - d.hop);
+        // large bands transform the centre of frames 2p and 2p+1 in one complex FFT, so a shard must also
+        // see the whole partner frame: one more hop on each side
+        p->halo = std::max<int64_t>(p->halo, d.n_fft > FUSED_MAX_N ? d.n_fft : d.n_fft - d.hop);
+        p->delay = std::max<int64_t>(p->delay, d.n_fft - d.hop);
         p->bands.push_back(b);
     }
     e = cudaMemcpy(p->tables, host.data(), (size_t)floats * sizeof(float), cudaMemcpyHostToDevice);
@@ -341,11 +345,11 @@ int upmix_process(const UpmixPlan* plan, const float* L, const float* R, int64_t
 
 // ---- block streaming ---------------------------------------------------------------------------
 // state layout (floats): [track][2][delay] input history, then per band [track][3][n_fft] rings.
-int64_t upmix_stream_delay(const UpmixPlan* plan) { return plan ? plan->halo : fail(UPMIX_E_INVALID, "plan is NULL"); }
+int64_t upmix_stream_delay(const UpmixPlan* plan) { return plan ? plan->delay : fail(UPMIX_E_INVALID, "plan is NULL"); }
 
 int64_t upmix_stream_state_bytes(const UpmixPlan* plan, int n_tracks) {
     if (!plan || n_tracks < 1) return fail(UPMIX_E_INVALID, "bad plan / n_tracks");
-    int64_t floats = round_up(2 * plan->halo * n_tracks, 64);
+    int64_t floats = round_up(2 * plan->delay * n_tracks, 64);
     for (const BandDev& b : plan->bands) floats += round_up(3LL * b.n_fft * n_tracks, 64);
     return floats * (int64_t)sizeof(float);
 }
@@ -359,7 +363,7 @@ int upmix_stream_reset(const UpmixPlan* plan, void* state, int n_tracks, void* s
 
 int64_t upmix_stream_workspace_bytes(const UpmixPlan* plan, int n_new, int n_tracks) {
     if (!plan || n_new < 1 || n_tracks < 1) return fail(UPMIX_E_INVALID, "bad arguments");
-    const int64_t stage = round_up(2LL * n_tracks * (plan->halo + n_new) * (int64_t)sizeof(float), 256);
+    const int64_t stage = round_up(2LL * n_tracks * (plan->delay + n_new) * (int64_t)sizeof(float), 256);
     return stage + make_layout(plan, n_new, n_tracks).total;
 }
 
@@ -379,7 +383,7 @@ int upmix_stream_block(const UpmixPlan* plan, void* state, int64_t samples_done,
     if (workspace_bytes < need) return fail(UPMIX_E_WORKSPACE, "workspace too small: %lld given, %lld needed", (long long)workspace_bytes, (long long)need);
     DeviceGuard guard(plan->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int64_t D = plan->halo;
+    const int64_t D = plan->delay;
     const int64_t span = D + n_new;
     float* hist = reinterpret_cast<float*>(state);
     float* stage = reinterpret_cast<float*>(workspace);       // [2][track][span]
@@ -422,6 +426,39 @@ int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, con
     const int64_t s0 = frame_index * b.hop;
     return run_segment(plan, blk_l, blk_r, s0, s0 + b.n_fft, INT64_MAX / 4, s0, s0 + b.hop, n_tracks, in_stride, out_c, out_l,
                        out_r, out_stride, workspace, workspace_bytes, rings, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int64_t upmix_debug_launch_count(int reset) { return (int64_t)launch_count(reset != 0); }
+
+int upmix_measure_fp32_tflops(int device, double* tflops, int* sm_count) {
+    if (!tflops) return fail(UPMIX_E_INVALID, "tflops is NULL");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(UPMIX_E_CUDA, "cannot select device %d", device);
+    int sms = 0;
+    CU_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (sm_count) *sm_count = sms;
+    float* out = nullptr;
+    CU_CHECK(cudaMalloc(&out, sizeof(float) * sms * 64));
+    cudaEvent_t e0, e1;
+    CU_CHECK(cudaEventCreate(&e0));
+    CU_CHECK(cudaEventCreate(&e1));
+    const int blocks = sms * 8 * 4, iters = 1 << 15;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CU_CHECK(cudaEventRecord(e0, nullptr));
+        CU_CHECK(launch_fma_peak(out, blocks, iters, nullptr));
+        CU_CHECK(cudaEventRecord(e1, nullptr));
+        CU_CHECK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return UPMIX_OK;
 }
 
 int upmix_process_host(const UpmixPlan* plan, const float* L, const float* R, int64_t n_samples, float* out_c,

@@ -401,8 +401,37 @@ __global__ void __launch_bounds__(256) band_sum_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// FP32 peak probe: 8 independent FMA chains per thread, enough warps to fill every SM.  Used by
+// bench.py for the roofline denominator (MEASURED_PEAKS.json has no FP32 figure).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float b, float c) {
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = (float)(threadIdx.x + j) * 1e-3f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = fmaf(a[j], b, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += a[j];
+    if (s == 123.456f) out[blockIdx.x] = s;       // never true in practice; keeps the chains alive
+}
+
+cudaError_t launch_fma_peak(float* out, int blocks, int iters, cudaStream_t st) {
+    fma_peak_kernel<<<blocks, 256, 0, st>>>(out, iters, 0.999f, 1e-4f);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers (called from upmix_capi.cu)
 // ---------------------------------------------------------------------------------------------
+static unsigned long long g_launches = 0;
+unsigned long long launch_count(bool reset) {
+    const unsigned long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
 template <int N>
 static cudaError_t launch_fused_n(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st) {
     static bool attr_done[64] = {};
@@ -415,6 +444,7 @@ static cudaError_t launch_fused_n(const BandDev& b, const SegArgs& a, int n_runs
         attr_done[dev & 63] = true;
     }
     band_fused_kernel<N><<<dim3(n_runs, n_tracks), FusedCfg<N>::T, FusedCfg<N>::SMEM, st>>>(b, a);
+    g_launches++;
     return cudaGetLastError();
 }
 
@@ -449,6 +479,7 @@ int fused_smem_bytes(int n_fft) {
 cudaError_t launch_col_fwd(const BandDev& b, const SegArgs& a, const WaveArgs& w, int n_tracks, cudaStream_t st) {
     const int n2 = b.n_fft / COL_R;
     col_fwd_kernel<<<dim3((n2 + 127) / 128, w.n_frames, n_tracks), 128, 0, st>>>(b, a, w);
+    g_launches++;
     return cudaGetLastError();
 }
 
@@ -464,6 +495,7 @@ static cudaError_t launch_row_n(const BandDev& b, const WaveArgs& w, int n_track
         attr_done[dev & 63] = true;
     }
     row_mask_kernel<N2><<<dim3(COL_R / 2, w.n_frames / 2, n_tracks), RowCfg<N2>::T, RowCfg<N2>::SMEM, st>>>(b, w);
+    g_launches++;
     return cudaGetLastError();
 }
 
@@ -480,6 +512,7 @@ cudaError_t launch_col_inv_ola(const BandDev& b, const SegArgs& a, const WaveArg
                                cudaStream_t st) {
     const int n2 = b.n_fft / COL_R;
     col_inv_ola_kernel<<<dim3((n2 + 127) / 128, n_runs, n_tracks), 128, 0, st>>>(b, a, w);
+    g_launches++;
     return cudaGetLastError();
 }
 
@@ -494,6 +527,7 @@ cudaError_t launch_band_sum(const float* ws, int n_bands, int n_tracks, long lon
     long long blocks = (nvec + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     dim3 grid((unsigned)blocks, n_tracks);
+    g_launches++;
     if (vec) band_sum_kernel<4><<<grid, 256, 0, st>>>(ws, n_bands, n_tracks, seg_len, ws_seg, out_c, out_l, out_r, out_stride, mode);
     else band_sum_kernel<1><<<grid, 256, 0, st>>>(ws, n_bands, n_tracks, seg_len, ws_seg, out_c, out_l, out_r, out_stride, mode);
     return cudaGetLastError();

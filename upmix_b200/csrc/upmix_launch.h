@@ -15,4 +15,7 @@ cudaError_t launch_band_sum(const float* ws, int n_bands, int n_tracks, long lon
                             float* out_c, float* out_l, float* out_r, long long out_stride, int mode,
                             cudaStream_t st);
 
+cudaError_t launch_fma_peak(float* out, int blocks, int iters, cudaStream_t st);
+unsigned long long launch_count(bool reset);
+
 }  // namespace upmix
