@@ -89,8 +89,8 @@ int upmix_process_segment(const UpmixPlan* plan, const float* L, const float* R,
                           float* out_c, float* out_l, float* out_r, int64_t out_stride, void* workspace,
                           int64_t workspace_bytes, void* stream);
 
-/* Input margin (samples each side) upmix_process_segment needs: max over bands of n_fft - hop, or of
- * n_fft for bands above 8192 (their frames are transformed in even/odd pairs). */
+/* Input margin (samples each side) upmix_process_segment needs: max over bands of n_fft, or of
+ * n_fft + hop for bands above 8192 (their frames are transformed in even/odd pairs). */
 int64_t upmix_segment_halo(const UpmixPlan* plan);
 
 /* Block streaming (bands with n_fft <= 8192).  `state` is caller-owned device memory of

@@ -173,8 +173,9 @@ def test_partition_invariance_segments_and_tracks(ce):
     for a, b in zip(cuts[:-1], cuts[1:]):
         lo, hi = max(0, a - halo), min(n, b + halo)
         seg = plan.process_segment(dl[lo:hi].contiguous(), dr[lo:hi].contiguous(), lo, n, a, b)
-        for w, s in zip(whole, seg):
-            assert torch.equal(w[a:b], s), (a, b)
+        for ch, (w, s) in enumerate(zip(whole, seg)):
+            d = (w[a:b] - s).abs()
+            assert torch.equal(w[a:b], s), (a, b, ch, float(d.max()), int(d.argmax()))
     # tracks: a batch of 3 different tracks == 3 single runs
     Ls = torch.stack([dl, dr, dl.flip(0)])
     Rs = torch.stack([dr, dl, dr * 0.5])

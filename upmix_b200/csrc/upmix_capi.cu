@@ -278,9 +278,11 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
             off += 2LL * d.n_fft;
             p->max_large_n = std::max(p->max_large_n, d.n_fft);
         }
-        // large bands transform the centre of frames 2p and 2p+1 in one complex FFT, so a shard must also
-        // see the whole partner frame: one more hop on each side
-        p->halo = std::max<int64_t>(p->halo, d.n_fft > FUSED_MAX_N ? d.n_fft : d.n_fft - d.hop);
+        // Margin a time shard needs around [seg_begin, seg_end): the first hop may start up to hop-1
+        // samples before seg_begin and needs the 3 frames before it -> n_fft; large bands transform the
+        // centre of frames 2p and 2p+1 in one complex FFT, so a shard must also see the whole partner
+        // frame -> one more hop.
+        p->halo = std::max<int64_t>(p->halo, d.n_fft > FUSED_MAX_N ? d.n_fft + d.hop : d.n_fft);
         p->delay = std::max<int64_t>(p->delay, d.n_fft - d.hop);
         p->bands.push_back(b);
     }
