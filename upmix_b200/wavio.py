@@ -1,0 +1,38 @@
+"""WAV input/output for main.py.  The reference uses `soundfile` (main.py:43,119); when it is not
+installed this falls back to scipy.io.wavfile / the standard library with the same conventions:
+reading returns float64 in [-1, 1) shaped [frames, channels] (soundfile's default dtype), writing
+stores 16-bit PCM (soundfile's default subtype for .wav)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def read_wav(path: str):
+    try:
+        import soundfile as sf
+        return sf.read(path)
+    except ImportError:
+        pass
+    from scipy.io import wavfile
+    sr, data = wavfile.read(path)
+    if data.dtype == np.int16:
+        wave = data.astype(np.float64) / 32768.0
+    elif data.dtype == np.int32:
+        wave = data.astype(np.float64) / 2147483648.0
+    elif data.dtype == np.uint8:
+        wave = (data.astype(np.float64) - 128.0) / 128.0
+    else:
+        wave = data.astype(np.float64)
+    return wave, int(sr)
+
+
+def write_wav(path: str, data: np.ndarray, sr: int) -> None:
+    try:
+        import soundfile as sf
+        sf.write(path, data, sr)
+        return
+    except ImportError:
+        pass
+    from scipy.io import wavfile
+    pcm = np.clip(np.asarray(data, dtype=np.float64), -1.0, 32767.0 / 32768.0)
+    wavfile.write(path, int(sr), np.round(pcm * 32768.0).astype(np.int16))
