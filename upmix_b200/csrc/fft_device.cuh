@@ -1,15 +1,19 @@
 // Shared-memory Stockham FFT building blocks for sm_100a (no cuFFT).
 //
 // A transform of N = R1*R2*...*Rp complex points lives in one shared-memory buffer of float2 and is
-// done in p auto-sorting (Stockham) passes.  In every pass a thread owns whole radix-R butterflies:
-// it reads R points at stride N/R (consecutive threads -> consecutive words, conflict-free),
-// multiplies by the pass twiddles, runs the radix-R DFT in registers and scatters the R results
-// at stride NS (the product of the radices already done).  The buffer is updated in place: all reads
-// of a pass finish (barrier) before its writes start.  Several independent rows can share the pass
-// (ROWS), which is how the row kernel of the large-N path batches its transforms.
+// done in p auto-sorting (Stockham) passes with large in-register radices (up to 32), so that a
+// transform of 8192 points needs only three passes (32*16*16) and two trips through shared memory.
+// In every pass a thread owns whole radix-R butterflies: it reads R points at stride N/R
+// (consecutive threads -> consecutive words, conflict-free), multiplies by the pass twiddles (read
+// coalesced from a per-pass table in global memory, L1/L2 resident and frame-invariant), runs the
+// radix-R DFT in registers and scatters the R results at stride NS (the product of the radices
+// already done).  The buffer is updated in place: all reads of a pass finish (barrier) before its
+// writes start.  Several independent rows can share the pass (ROWS), which is how the row kernel of
+// the large-N path batches its transforms.
 //
-// Index padding PAD(i) = i + (i >> 4) keeps the stride-R scatter of the early passes off the same
-// 8-byte bank (16 distinct double-banks per half-warp for LDS.64/STS.64).
+// Index padding PAD(i) = i + (i >> log2 R1) keeps the stride-R1 scatter of the first pass off the
+// same 8-byte bank (16 distinct double-banks per half-warp for STS.64); later passes have NS >= 16
+// and write runs of consecutive words.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,7 +25,6 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
 // multiply by DIR*i  (DIR = -1: forward transform, e^{-i...};  DIR = +1: inverse)
 template <int DIR>
@@ -29,26 +32,25 @@ __device__ __forceinline__ float2 mul_i(float2 a) {
     return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
 }
 
-// z * exp(DIR * 2*pi*i * m / 16), m in [0, 8), with the trivial cases folded away.
+// z * exp(DIR * 2*pi*i * m / 32), m in [0, 16), with the trivial cases folded away.
 template <int DIR>
-__device__ __forceinline__ float2 mul_w16(float2 z, int m) {
-    constexpr float C1 = 0.92387953251128674f;   // cos(pi/8)
-    constexpr float S1 = 0.38268343236508977f;   // sin(pi/8)
-    constexpr float H = 0.70710678118654752f;    // cos(pi/4)
+__device__ __forceinline__ float2 mul_w32(float2 z, int m) {
     constexpr float s = DIR < 0 ? -1.f : 1.f;
-    switch (m) {
-        case 0: return z;
-        case 1: return cmul(z, make_float2(C1, s * S1));
-        case 2: return make_float2(H * (z.x - s * z.y), H * (z.y + s * z.x));
-        case 3: return cmul(z, make_float2(S1, s * C1));
-        case 4: return mul_i<DIR>(z);
-        case 5: return cmul(z, make_float2(-S1, s * C1));
-        case 6: return make_float2(H * (-z.x - s * z.y), H * (s * z.x - z.y));
-        default: return cmul(z, make_float2(-C1, s * S1));
-    }
+    constexpr float H = 0.70710678118654752f;    // cos(pi/4)
+    // cos(2 pi m / 32), m = 0..8
+    constexpr float C[9] = {1.f, 0.98078528040323045f, 0.92387953251128676f, 0.83146961230254524f, 0.70710678118654752f,
+                            0.55557023301960222f, 0.38268343236508977f, 0.19509032201612827f, 0.f};
+    if (m == 0) return z;
+    if (m == 8) return mul_i<DIR>(z);
+    if (m == 4) return make_float2(H * (z.x - s * z.y), H * (z.y + s * z.x));
+    if (m == 12) return make_float2(H * (-z.x - s * z.y), H * (s * z.x - z.y));
+    // general: cos(2 pi m/32) = C[m] (m<8) or -C[16-m]; sin(2 pi m/32) = C[8-m] (m<8) or C[m-8]
+    const float c = m < 8 ? C[m] : -C[16 - m];
+    const float sn = m < 8 ? C[8 - m] : C[m - 8];
+    return cmul(z, make_float2(c, s * sn));
 }
 
-// In-register radix-R DFT, decimation in time, natural-order output.  R in {2,4,8,16}.
+// In-register radix-R DFT, decimation in time, natural-order output.  R in {2,4,8,16,32}.
 template <int R, int DIR>
 struct Dft {
     static __device__ __forceinline__ void run(float2 (&v)[R]) {
@@ -59,7 +61,7 @@ struct Dft {
         Dft<R / 2, DIR>::run(o);
 #pragma unroll
         for (int k = 0; k < R / 2; k++) {
-            const float2 t = mul_w16<DIR>(o[k], k * (16 / R));
+            const float2 t = mul_w32<DIR>(o[k], k * (32 / R));
             v[k] = cadd(e[k], t);
             v[k + R / 2] = csub(e[k], t);
         }
@@ -72,24 +74,48 @@ struct Dft<1, DIR> {
 
 __host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 
-// radix of the next pass when `rem` = N / NS points are still to be combined
-__host__ __device__ constexpr int pick_radix(int rem) {
-    const int l = ilog2(rem);
-    return (l >= 3 && l != 4) ? 8 : (l == 4 || l == 2) ? 4 : 2;
+// ---------------------------------------------------------------------------------------------
+// Radix plans.  A plan packs the radices of the passes, 6 bits each, first pass in the low bits.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int mkplan(int r0, int r1, int r2 = 0, int r3 = 0) {
+    return r0 | (r1 << 6) | (r2 << 12) | (r3 << 18);
 }
+__host__ __device__ constexpr int fft_radix(int plan, int p) { return p > 3 ? 0 : (plan >> (6 * p)) & 63; }
+__host__ __device__ constexpr int fft_num_passes(int plan) {
+    return fft_radix(plan, 1) == 0 ? 1 : fft_radix(plan, 2) == 0 ? 2 : fft_radix(plan, 3) == 0 ? 3 : 4;
+}
+// product of the radices of passes 0..p-1
+__host__ __device__ constexpr int fft_ns(int plan, int p) {
+    return p == 0 ? 1 : fft_ns(plan, p - 1) * fft_radix(plan, p - 1);
+}
+__host__ __device__ constexpr int fft_size(int plan) { return fft_ns(plan, fft_num_passes(plan)); }
+// offset (in float2) of pass p's twiddles inside the transform's table; pass 0 has none
+__host__ __device__ constexpr int fft_tw_offset(int plan, int p) {
+    return p <= 1 ? 0 : fft_tw_offset(plan, p - 1) + (fft_radix(plan, p - 1) - 1) * fft_ns(plan, p - 1);
+}
+// total twiddle entries of a transform: table[off_p + (r-1)*NS_p + k] = exp(-2 pi i r k / (NS_p R_p))
+__host__ __device__ constexpr int fft_tw_size(int plan) { return fft_tw_offset(plan, fft_num_passes(plan)); }
 
-__host__ __device__ constexpr int PAD(int i) { return i + (i >> 4); }
-__host__ __device__ constexpr int PADSZ(int n) { return n + (n >> 4); }
+__host__ __device__ constexpr int pad_shift(int plan) { return ilog2(fft_radix(plan, 0)); }
+template <int PLAN>
+__host__ __device__ constexpr int PAD(int i) { return i + (i >> pad_shift(PLAN)); }
+template <int PLAN>
+__host__ __device__ constexpr int PADSZ() { return fft_size(PLAN) + (fft_size(PLAN) >> pad_shift(PLAN)); }
 
-// One Stockham pass over ROWS rows of N points held in `buf` (row stride PADSZ(N)).
+// One Stockham pass over ROWS rows of N points held in `buf` (row stride PADSZ<N>()).
 //   FIRST: inputs come from ld(row, idx) instead of buf;  LAST: outputs go to st(row, idx, v).
-//   tw[m * tws] = exp(-2*pi*i*m/N)  (forward table; conjugated here for DIR = +1).
-template <int N, int R, int NS, int DIR, int T, int ROWS, bool FIRST, bool LAST, bool LD_SMEM, class Ld, class St>
-__device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2* __restrict__ tw, int tws,
-                                              Ld& ld, St& st) {
+//   tw: this transform's twiddle table (forward sign; conjugated here for DIR = +1).
+template <int PLAN, int P, int DIR, int T, int ROWS, bool LD_SMEM, class Ld, class St>
+__device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2* __restrict__ tw, Ld& ld, St& st) {
+    constexpr int N = fft_size(PLAN);
+    constexpr int R = fft_radix(PLAN, P);
+    constexpr int NS = fft_ns(PLAN, P);
+    constexpr bool FIRST = P == 0;
+    constexpr bool LAST = NS * R == N;
     constexpr int NB = N / R;                      // butterflies per row
     constexpr int TOTAL = NB * ROWS;
     constexpr int IT = (TOTAL + T - 1) / T;
+    constexpr int RS = PADSZ<PLAN>();
     float2 v[IT][R];
 #pragma unroll
     for (int it = 0; it < IT; it++) {
@@ -100,7 +126,7 @@ __device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 if (FIRST) v[it][r] = ld(row, j + r * NB);
-                else v[it][r] = buf[row * PADSZ(N) + PAD(j + r * NB)];
+                else v[it][r] = buf[row * RS + PAD<PLAN>(j + r * NB)];
             }
         }
     }
@@ -113,10 +139,10 @@ __device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2
             const int j = ROWS == 1 ? jj : jj - row * NB;
             const int k = j & (NS - 1);
             if (NS > 1) {
-                constexpr int step = N / (NS * R);
+                const float2* __restrict__ twp = tw + fft_tw_offset(PLAN, P) + k;
 #pragma unroll
                 for (int r = 1; r < R; r++) {
-                    float2 w = __ldg(&tw[(r * k * step) * tws]);
+                    float2 w = __ldg(twp + (r - 1) * NS);
                     if (DIR > 0) w.y = -w.y;
                     v[it][r] = cmul(v[it][r], w);
                 }
@@ -126,30 +152,27 @@ __device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 if (LAST) st(row, j0 + r * NS, v[it][r]);
-                else buf[row * PADSZ(N) + PAD(j0 + r * NS)] = v[it][r];
+                else buf[row * RS + PAD<PLAN>(j0 + r * NS)] = v[it][r];
             }
         }
     }
     __syncthreads();
 }
 
-template <int N, int NS, int DIR, int T, int ROWS, bool LD_SMEM, class Ld, class St>
-__device__ __forceinline__ void stockham_rec(float2* buf, int tid, const float2* __restrict__ tw, int tws,
-                                             Ld& ld, St& st) {
-    constexpr int R = pick_radix(N / NS);
-    constexpr bool LAST = (NS * R == N);
-    stockham_pass<N, R, NS, DIR, T, ROWS, NS == 1, LAST, LD_SMEM, Ld, St>(buf, tid, tw, tws, ld, st);
-    if constexpr (!LAST) stockham_rec<N, NS * R, DIR, T, ROWS, LD_SMEM, Ld, St>(buf, tid, tw, tws, ld, st);
+template <int PLAN, int P, int DIR, int T, int ROWS, bool LD_SMEM, class Ld, class St>
+__device__ __forceinline__ void stockham_rec(float2* buf, int tid, const float2* __restrict__ tw, Ld& ld, St& st) {
+    stockham_pass<PLAN, P, DIR, T, ROWS, LD_SMEM, Ld, St>(buf, tid, tw, ld, st);
+    if constexpr (P + 1 < fft_num_passes(PLAN)) stockham_rec<PLAN, P + 1, DIR, T, ROWS, LD_SMEM, Ld, St>(buf, tid, tw, ld, st);
 }
 
-// Full transform of ROWS rows.  ld(row, n) supplies input point n; st(row, k, value) receives output
-// point k (natural order).  LD_SMEM says ld reads the same shared buffer (forces the read barrier).
-// Ends with a __syncthreads().
-template <int N, int DIR, int T, int ROWS, bool LD_SMEM, class Ld, class St>
-__device__ __forceinline__ void fft_smem(float2* buf, int tid, const float2* __restrict__ tw, int tws,
-                                         Ld ld, St st) {
-    static_assert(N >= 8, "transform too small");
-    stockham_rec<N, 1, DIR, T, ROWS, LD_SMEM, Ld, St>(buf, tid, tw, tws, ld, st);
+// Full transform of ROWS rows of fft_size(PLAN) points.  ld(row, n) supplies input point n; st(row, k,
+// value) receives output point k (natural order).  LD_SMEM says ld reads the same shared buffer
+// (forces the read barrier).  tw = twiddle table of THIS plan (fft_tw_size(PLAN) entries).  Ends with
+// a __syncthreads().
+template <int PLAN, int DIR, int T, int ROWS, bool LD_SMEM, class Ld, class St>
+__device__ __forceinline__ void fft_smem(float2* buf, int tid, const float2* __restrict__ tw, Ld ld, St st) {
+    static_assert(fft_num_passes(PLAN) >= 2, "a plan needs at least two passes");
+    stockham_rec<PLAN, 0, DIR, T, ROWS, LD_SMEM, Ld, St>(buf, tid, tw, ld, st);
 }
 
 // ---------------------------------------------------------------------------------------------

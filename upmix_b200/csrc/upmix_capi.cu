@@ -12,6 +12,7 @@
 #include <new>
 #include <vector>
 
+#include "fft_device.cuh"
 #include "upmix_kernels.cuh"
 #include "upmix_launch.h"
 
@@ -209,7 +210,7 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
     *out = nullptr;
     if (n_bands < 1 || !bands) return fail(UPMIX_E_INVALID, "need at least one band");
     if (out_mode != UPMIX_OUT_LSCRS && out_mode != UPMIX_OUT_FOLD) return fail(UPMIX_E_INVALID, "unknown out_mode %d", out_mode);
-    int64_t floats = 2 * TW_N;   // master twiddles
+    int64_t floats = 0;
     for (int i = 0; i < n_bands; i++) {
         const UpmixBandDesc& d = bands[i];
         if (!d.ana || !d.syn || !d.gain) return fail(UPMIX_E_INVALID, "band %d: NULL table", i);
@@ -220,7 +221,14 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
         if (d.n_fft > FUSED_MAX_N && d.hop * 4 != d.n_fft)
             return fail(UPMIX_E_UNSUPPORTED, "band %d: n_fft=%d > %d requires hop = n_fft/4 (75%% overlap), got %d", i, d.n_fft, FUSED_MAX_N, d.hop);
         floats += round_up(d.n_fft, 64) * 2 + round_up(d.n_fft / 2 + 1, 64);
-        if (d.n_fft > FUSED_MAX_N) floats += 2LL * d.n_fft;
+        if (d.n_fft > FUSED_MAX_N) {
+            floats += 2LL * d.n_fft + round_up(2LL * fft_tw_size(row_plan(d.n_fft / COL_R)), 64);
+        } else {
+            int pf = 0, ph = 0;
+            fused_plans(d.n_fft, &pf, &ph);
+            floats += round_up(2LL * fft_tw_size(pf), 64) + round_up(2LL * fft_tw_size(ph), 64) +
+                      round_up(2LL * (d.n_fft / 4 + 1), 64);
+        }
     }
     DeviceGuard guard(device);
     if (!guard.ok) return fail(UPMIX_E_CUDA, "cannot select device %d", device);
@@ -238,23 +246,24 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
     }
     float* dbase = reinterpret_cast<float*>(p->tables);
     int64_t off = 0;
-    // master twiddles, double precision -> float32, exact at the octant points
-    for (int m = 0; m < TW_N; m++) {
-        const double ang = -2.0 * M_PI * (double)m / (double)TW_N;
-        double c = cos(ang), s = sin(ang);
-        if (m % (TW_N / 4) == 0) { c = (m == 0) ? 1.0 : (m == TW_N / 2 ? -1.0 : 0.0); s = (m == TW_N / 4) ? -1.0 : (m == 3 * TW_N / 4 ? 1.0 : 0.0); }
-        host[2 * m] = (float)c;
-        host[2 * m + 1] = (float)s;
-    }
-    const float2* d_tw = reinterpret_cast<const float2*>(dbase);
-    off += 2 * TW_N;
+    // per-pass FFT twiddles of an n-point transform (layout: fft_device.cuh), double -> float32
+    auto gen_fft_tw = [&](int plan, float* dst) {
+        for (int pass = 1; pass < fft_num_passes(plan); pass++) {
+            const int R = fft_radix(plan, pass), NS = fft_ns(plan, pass), o = fft_tw_offset(plan, pass);
+            for (int r = 1; r < R; r++)
+                for (int k = 0; k < NS; k++) {
+                    const double ang = -2.0 * M_PI * (double)(((int64_t)r * k) % ((int64_t)NS * R)) / ((double)NS * R);
+                    dst[2 * (o + (r - 1) * NS + k)] = (float)cos(ang);
+                    dst[2 * (o + (r - 1) * NS + k) + 1] = (float)sin(ang);
+                }
+        }
+    };
     for (int i = 0; i < n_bands; i++) {
         const UpmixBandDesc& d = bands[i];
         BandDev b;
         b.n_fft = d.n_fft;
         b.hop = d.hop;
-        b.tw = d_tw;
-        b.tw_col = nullptr;
+        b.tw_fft = b.tw_half = b.tw_pack = b.tw_col = nullptr;
         memcpy(&host[off], d.ana, sizeof(float) * d.n_fft);
         b.ana = dbase + off;
         off += round_up(d.n_fft, 64);
@@ -265,8 +274,27 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
         memcpy(&host[off], d.gain, sizeof(float) * (d.n_fft / 2 + 1));
         b.gain = dbase + off;
         off += round_up(d.n_fft / 2 + 1, 64);
-        if (d.n_fft > FUSED_MAX_N) {
+        if (d.n_fft <= FUSED_MAX_N) {
+            int pf = 0, ph = 0;
+            fused_plans(d.n_fft, &pf, &ph);
+            gen_fft_tw(pf, &host[off]);
+            b.tw_fft = reinterpret_cast<const float2*>(dbase + off);
+            off += round_up(2LL * fft_tw_size(pf), 64);
+            gen_fft_tw(ph, &host[off]);
+            b.tw_half = reinterpret_cast<const float2*>(dbase + off);
+            off += round_up(2LL * fft_tw_size(ph), 64);
+            for (int k = 0; k <= d.n_fft / 4; k++) {
+                const double ang = -2.0 * M_PI * (double)k / (double)d.n_fft;
+                host[off + 2 * k] = (float)cos(ang);
+                host[off + 2 * k + 1] = (float)sin(ang);
+            }
+            b.tw_pack = reinterpret_cast<const float2*>(dbase + off);
+            off += round_up(2LL * (d.n_fft / 4 + 1), 64);
+        } else {
             const int n2 = d.n_fft / COL_R;
+            gen_fft_tw(row_plan(n2), &host[off]);
+            b.tw_fft = reinterpret_cast<const float2*>(dbase + off);
+            off += round_up(2LL * fft_tw_size(row_plan(n2)), 64);
             for (int k1 = 0; k1 < COL_R; k1++)
                 for (int c = 0; c < n2; c++) {
                     const int64_t m = ((int64_t)k1 * c) % d.n_fft;

@@ -22,22 +22,33 @@ namespace upmix {
 // ---------------------------------------------------------------------------------------------
 // fused single-CTA band kernel
 // ---------------------------------------------------------------------------------------------
-template <int N>
-struct FusedCfg {
-    static constexpr int T = (N / 8 < 32) ? 32 : (N / 8 > 512 ? 512 : N / 8);
-    static constexpr int MINB = 512 / T;          // caps registers at 128 per thread
-    static constexpr int SMEM = (PADSZ(N) + PADSZ(N / 2)) * (int)sizeof(float2) + 3 * N * (int)sizeof(float);
-};
+// Per-size configuration of the fused kernel: radix plans of the N-point and N/2-point transforms,
+// threads per CTA (= per frame in flight) and the CTAs per SM the register budget is sized for.
+template <int N> struct FusedCfg;
+#define UPMIX_FUSED_CFG(N_, FULL_, HALF_, T_, MINB_)                                                     \
+    template <> struct FusedCfg<N_> {                                                                     \
+        static constexpr int FULL = FULL_, HALF = HALF_, T = T_, MINB = MINB_;                            \
+        static_assert(fft_size(FULL_) == N_ && fft_size(HALF_) == N_ / 2, "plan does not match the size"); \
+        static constexpr int SMEM = (PADSZ<FULL_>() + PADSZ<HALF_>()) * (int)sizeof(float2) + 3 * N_ * (int)sizeof(float); \
+    };
+UPMIX_FUSED_CFG(64, mkplan(8, 8), mkplan(8, 4), 32, 16)
+UPMIX_FUSED_CFG(128, mkplan(16, 8), mkplan(8, 8), 32, 8)
+UPMIX_FUSED_CFG(256, mkplan(16, 16), mkplan(16, 8), 32, 8)
+UPMIX_FUSED_CFG(512, mkplan(32, 16), mkplan(16, 16), 32, 8)
+UPMIX_FUSED_CFG(1024, mkplan(32, 32), mkplan(32, 16), 32, 8)
+UPMIX_FUSED_CFG(2048, mkplan(16, 16, 8), mkplan(16, 16, 4), 128, 4)
+UPMIX_FUSED_CFG(4096, mkplan(16, 16, 16), mkplan(16, 16, 8), 256, 2)
+UPMIX_FUSED_CFG(8192, mkplan(32, 16, 16), mkplan(16, 16, 16), 256, 1)
 
 template <int N>
 __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_kernel(const BandDev b, const SegArgs a) {
     constexpr int T = FusedCfg<N>::T;
     constexpr int M = N / 2;
-    constexpr int TWS = TW_N / N;
+    constexpr int PF = FusedCfg<N>::FULL, PH = FusedCfg<N>::HALF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* Z = reinterpret_cast<float2*>(smem_raw);
-    float2* Cz = Z + PADSZ(N);
-    float* ring = reinterpret_cast<float*>(Cz + PADSZ(M));   // [3][N]: C, Ls, Rs
+    float2* Cz = Z + PADSZ<PF>();
+    float* ring = reinterpret_cast<float*>(Cz + PADSZ<PH>());   // [3][N]: C, Ls, Rs
 
     const int tid = threadIdx.x;
     const int H = b.hop;
@@ -69,65 +80,82 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
     const float* __restrict__ ana = b.ana;
     const float* __restrict__ syn = b.syn;
     const float* __restrict__ gain = b.gain;
-    const float2* __restrict__ tw = b.tw;
+    const float2* __restrict__ tw = b.tw_fft;
+    const float2* __restrict__ twh = b.tw_half;
+    const float2* __restrict__ twp = b.tw_pack;
 
     for (long long f = f_begin; f < h1; ++f) {
         const long long s0 = f * H;
         const int base = (int)(f % K) * H;
 
         // ---- forward: Z = FFT_N( ana * (L + iR) ) -----------------------------------------------
+        // unconditional (clamped) loads so that the whole batch is in flight at once; samples outside
+        // [in_begin, in_end) -- before the track, past its end, or another shard's -- read as zero
         auto ld_in = [&](int, int n) -> float2 {
             const long long s = s0 + n;
-            if (s >= a.in_begin && s < a.in_end) {
-                const float w = __ldg(ana + n);
-                return make_float2(__ldg(inl + (s - a.in_begin)) * w, __ldg(inr + (s - a.in_begin)) * w);
-            }
-            return make_float2(0.f, 0.f);
+            const bool ok = s >= a.in_begin && s < a.in_end;
+            const long long idx = ok ? s - a.in_begin : 0;
+            const float w = __ldg(ana + n);
+            const float l = __ldg(inl + idx), r = __ldg(inr + idx);
+            return ok ? make_float2(l * w, r * w) : make_float2(0.f, 0.f);
         };
-        auto st_z = [&](int, int k, float2 v) { Z[PAD(k)] = v; };
-        fft_smem<N, -1, T, 1, false>(Z, tid, tw, TWS, ld_in, st_z);
+        auto st_z = [&](int, int k, float2 v) { Z[PAD<PF>(k)] = v; };
+        fft_smem<PF, -1, T, 1, false>(Z, tid, tw, ld_in, st_z);
 
         // ---- split / gain / mask; Y1 = Ls + i*Rs in place, C packed for the half-size inverse ---
-        for (int k = tid; k <= M / 2; k += T) {
-            const int k2 = M - k;
-            const int km = (N - k) & (N - 1);
-            const float2 a1 = Z[PAD(k)], b1 = Z[PAD(km)];
-            const float2 a2 = Z[PAD(k2)], b2 = Z[PAD(M + k)];
-            const float g1 = __ldg(gain + k), g2 = __ldg(gain + k2);
-            float2 c1 = make_float2(0.f, 0.f), l1 = c1, r1 = c1, c2 = c1, l2 = c1, r2 = c1;
-            if (g1 != 0.f) split_gain_mask(a1, b1, g1, c1, l1, r1);
-            if (g2 != 0.f) split_gain_mask(a2, b2, g2, c2, l2, r2);
-            Z[PAD(k)] = make_float2(l1.x - r1.y, l1.y + r1.x);
-            Z[PAD(km)] = make_float2(l1.x + r1.y, r1.x - l1.y);
-            Z[PAD(k2)] = make_float2(l2.x - r2.y, l2.y + r2.x);
-            Z[PAD(M + k)] = make_float2(l2.x + r2.y, r2.x - l2.y);
-            // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);  IFFT_M(z)[m] = c[2m] + i c[2m+1]
-            const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
-            const float2 B = make_float2(c1.x - c2.x, c1.y + c2.y);
-            const float2 w = __ldg(tw + k * TWS);
-            const float2 D = cmul(B, make_float2(w.x, -w.y));
-            Cz[PAD(k)] = make_float2(A.x - D.y, A.y + D.x);
-            if (k > 0) Cz[PAD(M - k)] = make_float2(A.x + D.y, D.x - A.y);
+        {
+            constexpr int ITM = (M / 2 + 1 + T - 1) / T;
+            float g1[ITM], g2[ITM];
+            float2 wp[ITM];
+#pragma unroll
+            for (int it = 0; it < ITM; it++) {          // table loads first, all in flight together
+                const int k = min(tid + it * T, M / 2);
+                g1[it] = __ldg(gain + k);
+                g2[it] = __ldg(gain + M - k);
+                wp[it] = __ldg(twp + k);
+            }
+#pragma unroll
+            for (int it = 0; it < ITM; it++) {
+                const int k = tid + it * T;
+                if (k > M / 2) break;
+                const int k2 = M - k;
+                const int km = (N - k) & (N - 1);
+                const float2 a1 = Z[PAD<PF>(k)], b1 = Z[PAD<PF>(km)];
+                const float2 a2 = Z[PAD<PF>(k2)], b2 = Z[PAD<PF>(M + k)];
+                float2 c1 = make_float2(0.f, 0.f), l1 = c1, r1 = c1, c2 = c1, l2 = c1, r2 = c1;
+                if (g1[it] != 0.f) split_gain_mask(a1, b1, g1[it], c1, l1, r1);
+                if (g2[it] != 0.f) split_gain_mask(a2, b2, g2[it], c2, l2, r2);
+                Z[PAD<PF>(k)] = make_float2(l1.x - r1.y, l1.y + r1.x);
+                Z[PAD<PF>(km)] = make_float2(l1.x + r1.y, r1.x - l1.y);
+                Z[PAD<PF>(k2)] = make_float2(l2.x - r2.y, l2.y + r2.x);
+                Z[PAD<PF>(M + k)] = make_float2(l2.x + r2.y, r2.x - l2.y);
+                // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);  IFFT_M(z)[m] = c[2m] + i c[2m+1]
+                const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
+                const float2 B = make_float2(c1.x - c2.x, c1.y + c2.y);
+                const float2 D = cmul(B, make_float2(wp[it].x, -wp[it].y));
+                Cz[PAD<PH>(k)] = make_float2(A.x - D.y, A.y + D.x);
+                if (k > 0) Cz[PAD<PH>(M - k)] = make_float2(A.x + D.y, D.x - A.y);
+            }
         }
         __syncthreads();
 
         // ---- inverse transforms, synthesis window, overlap-add (oldest frame first) --------------
-        auto ld_z = [&](int, int n) -> float2 { return Z[PAD(n)]; };
+        auto ld_z = [&](int, int n) -> float2 { return Z[PAD<PF>(n)]; };
         auto st_lr = [&](int, int n, float2 v) {
             const float w = __ldg(syn + n);
             const int p = (base + n) & (N - 1);
             ring[N + p] += v.x * w;
             ring[2 * N + p] += v.y * w;
         };
-        fft_smem<N, +1, T, 1, true>(Z, tid, tw, TWS, ld_z, st_lr);
-        auto ld_c = [&](int, int n) -> float2 { return Cz[PAD(n)]; };
+        fft_smem<PF, +1, T, 1, true>(Z, tid, tw, ld_z, st_lr);
+        auto ld_c = [&](int, int n) -> float2 { return Cz[PAD<PH>(n)]; };
         auto st_c = [&](int, int m, float2 v) {
             const int n = 2 * m;
             const int p = (base + n) & (N - 1);
             ring[p] += v.x * __ldg(syn + n);
             ring[p + 1] += v.y * __ldg(syn + n + 1);
         };
-        fft_smem<M, +1, T, 1, true>(Cz, tid, tw, 2 * TWS, ld_c, st_c);
+        fft_smem<PH, +1, T, 1, true>(Cz, tid, twh, ld_c, st_c);
 
         // ---- emit the hop this frame finished, clear its ring slots --------------------------------
         const bool emit = f >= h0;
@@ -173,12 +201,11 @@ __global__ void __launch_bounds__(128) col_fwd_kernel(const BandDev b, const Seg
     for (int r = 0; r < COL_R; r++) {
         const int n = r * N2 + n2;
         const long long s = s0 + n;
-        if (s >= a.in_begin && s < a.in_end) {
-            const float wn = __ldg(b.ana + n);
-            v[r] = make_float2(__ldg(inl + (s - a.in_begin)) * wn, __ldg(inr + (s - a.in_begin)) * wn);
-        } else {
-            v[r] = make_float2(0.f, 0.f);
-        }
+        const bool ok = s >= a.in_begin && s < a.in_end;
+        const long long idx = ok ? s - a.in_begin : 0;
+        const float wn = __ldg(b.ana + n);
+        const float l = __ldg(inl + idx), rr = __ldg(inr + idx);
+        v[r] = ok ? make_float2(l * wn, rr * wn) : make_float2(0.f, 0.f);
     }
     Dft<COL_R, -1>::run(v);
     float2* dst = w.a + (((long long)track * w.n_frames + fl) * COL_R) * N2 + n2;
@@ -187,11 +214,17 @@ __global__ void __launch_bounds__(128) col_fwd_kernel(const BandDev b, const Seg
     for (int k1 = 1; k1 < COL_R; k1++) dst[(long long)k1 * N2] = cmul(v[k1], __ldg(b.tw_col + k1 * N2 + n2));
 }
 
-template <int N2>
-struct RowCfg {
-    static constexpr int T = (N2 / 4 > 512) ? 512 : N2 / 4;
-    static constexpr int SMEM = 6 * PADSZ(N2) * (int)sizeof(float2);
-};
+template <int N2> struct RowCfg;
+#define UPMIX_ROW_CFG(N2_, PLAN_)                                                                \
+    template <> struct RowCfg<N2_> {                                                              \
+        static constexpr int PLAN = PLAN_;                                                        \
+        static_assert(fft_size(PLAN_) == N2_, "plan does not match the size");                   \
+        static constexpr int T = 2 * N2_ / fft_radix(PLAN_, 0); /* two rows, one butterfly each */ \
+        static constexpr int SMEM = 6 * PADSZ<PLAN_>() * (int)sizeof(float2);                     \
+    };
+UPMIX_ROW_CFG(1024, mkplan(16, 16, 4))
+UPMIX_ROW_CFG(2048, mkplan(16, 16, 8))
+UPMIX_ROW_CFG(4096, mkplan(16, 16, 16))
 
 // K2: one CTA per (row pair, frame pair, track).  Rows k1 and 16-k1 of the frame's spectrum are
 // mirror images of each other (bin k <-> N-k), so the CTA holds both rows of both frames, finishes
@@ -200,8 +233,8 @@ struct RowCfg {
 template <int N2>
 __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b, const WaveArgs w) {
     constexpr int T = RowCfg<N2>::T;
-    constexpr int TWS = TW_N / N2;
-    constexpr int RS = PADSZ(N2);
+    constexpr int PL = RowCfg<N2>::PLAN;
+    constexpr int RS = PADSZ<PL>();
     constexpr int N = COL_R * N2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* S = reinterpret_cast<float2*>(smem_raw);   // 6 rows: f0a f0b f1a f1b ca cb
@@ -212,7 +245,7 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
     const int ka = pr, kb = pr == 0 ? COL_R / 2 : COL_R - pr;
     const long long fbase = ((long long)track * w.n_frames + 2 * fp) * COL_R;
     const float2* __restrict__ A = w.a;
-    const float2* __restrict__ tw = b.tw;
+    const float2* __restrict__ tw = b.tw_fft;
     const float* __restrict__ gain = b.gain;
 
     // forward row transforms: rows (f0,ka) (f0,kb) then (f1,ka) (f1,kb)
@@ -223,39 +256,53 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
             return A[(fbase + (long long)g * COL_R + k1) * N2 + n];
         };
         float2* buf = S + 2 * g * RS;
-        auto st = [&](int row, int k, float2 v) { buf[row * RS + PAD(k)] = v; };
-        fft_smem<N2, -1, T, 2, false>(buf, tid, tw, TWS, ld, st);
+        auto st = [&](int row, int k, float2 v) { buf[row * RS + PAD<PL>(k)] = v; };
+        fft_smem<PL, -1, T, 2, false>(buf, tid, tw, ld, st);
     }
 
     // split / gain / mask over mirror pairs
     const int n_items = pr == 0 ? N2 + 1 : N2;
-    for (int it = tid; it < n_items; it += T) {
-        int lo_row, lo_idx, hi_row, hi_idx, bin;
-        if (pr != 0) {
-            const int k2 = it;
-            if (k2 < N2 / 2) { lo_row = 0; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = ka + COL_R * k2; }
-            else { lo_row = 1; lo_idx = N2 - 1 - k2; hi_row = 0; hi_idx = k2; bin = kb + COL_R * (N2 - 1 - k2); }
-        } else if (it <= N2 / 2) {          // row 0: bin 16*k2 <-> 16*(N2-k2)
-            lo_row = 0; lo_idx = it; hi_row = 0; hi_idx = (N2 - it) & (N2 - 1); bin = COL_R * it;
-        } else {                            // row 8: bin 8+16*k2 <-> 8+16*(N2-1-k2)
-            const int k2 = it - (N2 / 2 + 1);
-            lo_row = 1; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = COL_R / 2 + COL_R * k2;
-        }
-        const int lo = lo_row * RS + PAD(lo_idx), hi = hi_row * RS + PAD(hi_idx);
-        const float g = __ldg(gain + bin);
-        float2 c[2];
+    {
+        constexpr int ITM = (N2 + 1 + T - 1) / T;
+        int lo_a[ITM], hi_a[ITM];
+        float g_a[ITM];
 #pragma unroll
-        for (int fr = 0; fr < 2; fr++) {
-            float2* buf = S + 2 * fr * RS;
-            float2 ls = make_float2(0.f, 0.f), rs = ls;
-            c[fr] = ls;
-            if (g != 0.f) split_gain_mask(buf[lo], buf[hi], g, c[fr], ls, rs);
-            buf[lo] = make_float2(ls.x - rs.y, ls.y + rs.x);
-            buf[hi] = make_float2(ls.x + rs.y, rs.x - ls.y);
+        for (int i = 0; i < ITM; i++) {                 // index arithmetic and gain loads first
+            const int it = min(tid + i * T, n_items - 1);
+            int lo_row, lo_idx, hi_row, hi_idx, bin;
+            if (pr != 0) {
+                const int k2 = it;
+                if (k2 < N2 / 2) { lo_row = 0; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = ka + COL_R * k2; }
+                else { lo_row = 1; lo_idx = N2 - 1 - k2; hi_row = 0; hi_idx = k2; bin = kb + COL_R * (N2 - 1 - k2); }
+            } else if (it <= N2 / 2) {          // row 0: bin 16*k2 <-> 16*(N2-k2)
+                lo_row = 0; lo_idx = it; hi_row = 0; hi_idx = (N2 - it) & (N2 - 1); bin = COL_R * it;
+            } else {                            // row 8: bin 8+16*k2 <-> 8+16*(N2-1-k2)
+                const int k2 = it - (N2 / 2 + 1);
+                lo_row = 1; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = COL_R / 2 + COL_R * k2;
+            }
+            lo_a[i] = lo_row * RS + PAD<PL>(lo_idx);
+            hi_a[i] = hi_row * RS + PAD<PL>(hi_idx);
+            g_a[i] = __ldg(gain + bin);
         }
-        float2* cb = S + 4 * RS;
-        cb[lo] = make_float2(c[0].x - c[1].y, c[0].y + c[1].x);
-        cb[hi] = make_float2(c[0].x + c[1].y, c[1].x - c[0].y);
+#pragma unroll
+        for (int i = 0; i < ITM; i++) {
+            if (tid + i * T >= n_items) break;
+            const int lo = lo_a[i], hi = hi_a[i];
+            const float g = g_a[i];
+            float2 c[2];
+#pragma unroll
+            for (int fr = 0; fr < 2; fr++) {
+                float2* buf = S + 2 * fr * RS;
+                float2 ls = make_float2(0.f, 0.f), rs = ls;
+                c[fr] = ls;
+                if (g != 0.f) split_gain_mask(buf[lo], buf[hi], g, c[fr], ls, rs);
+                buf[lo] = make_float2(ls.x - rs.y, ls.y + rs.x);
+                buf[hi] = make_float2(ls.x + rs.y, rs.x - ls.y);
+            }
+            float2* cb = S + 4 * RS;
+            cb[lo] = make_float2(c[0].x - c[1].y, c[0].y + c[1].x);
+            cb[hi] = make_float2(c[0].x + c[1].y, c[1].x - c[0].y);
+        }
     }
     __syncthreads();
 
@@ -263,14 +310,14 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 #pragma unroll
     for (int g = 0; g < 3; g++) {
         float2* buf = S + 2 * g * RS;
-        auto ld = [&](int row, int n) -> float2 { return buf[row * RS + PAD(n)]; };
+        auto ld = [&](int row, int n) -> float2 { return buf[row * RS + PAD<PL>(n)]; };
         float2* dst = g < 2 ? w.b1 + (fbase + (long long)g * COL_R) * N2
                             : w.b2 + (((long long)track * (w.n_frames / 2) + fp) * COL_R) * N2;
         auto st = [&](int row, int n, float2 v) {
             const int k1 = row ? kb : ka;
             dst[(long long)k1 * N2 + n] = v;
         };
-        fft_smem<N2, +1, T, 2, true>(buf, tid, tw, TWS, ld, st);
+        fft_smem<PL, +1, T, 2, true>(buf, tid, tw, ld, st);
     }
     (void)N;
 }
@@ -459,6 +506,26 @@ cudaError_t launch_band_fused(const BandDev& b, const SegArgs& a, int n_runs, in
         case 4096: return launch_fused_n<4096>(b, a, n_runs, n_tracks, st);
         case 8192: return launch_fused_n<8192>(b, a, n_runs, n_tracks, st);
         default: return cudaErrorInvalidValue;
+    }
+}
+
+// radix plans, for the host-side twiddle tables
+void fused_plans(int n_fft, int* full, int* half) {
+    *full = *half = 0;
+    switch (n_fft) {
+#define UPMIX_CASE(N_) case N_: *full = FusedCfg<N_>::FULL; *half = FusedCfg<N_>::HALF; break;
+        UPMIX_CASE(64) UPMIX_CASE(128) UPMIX_CASE(256) UPMIX_CASE(512) UPMIX_CASE(1024) UPMIX_CASE(2048)
+        UPMIX_CASE(4096) UPMIX_CASE(8192)
+#undef UPMIX_CASE
+        default: break;
+    }
+}
+int row_plan(int n2) {
+    switch (n2) {
+        case 1024: return RowCfg<1024>::PLAN;
+        case 2048: return RowCfg<2048>::PLAN;
+        case 4096: return RowCfg<4096>::PLAN;
+        default: return 0;
     }
 }
 

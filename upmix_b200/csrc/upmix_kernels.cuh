@@ -9,7 +9,6 @@
 
 namespace upmix {
 
-constexpr int TW_N = 8192;        // master twiddle table: tw[m] = exp(-2*pi*i*m/TW_N)
 constexpr int COL_R = 16;         // column radix of the large-N (four-step) path
 constexpr int FUSED_MAX_N = 8192; // largest STFT size handled by the single-CTA fused kernel
 constexpr int LARGE_MAX_N = 65536;
@@ -21,7 +20,10 @@ struct BandDev {
     const float* ana;          // [n_fft]       analysis window
     const float* syn;          // [n_fft]       synthesis window / n_fft (the inverse FFT is unnormalised)
     const float* gain;         // [n_fft/2+1]   band-limit gain
-    const float2* tw;          // [TW_N]        master twiddles
+    const float2* tw_fft;      // per-pass twiddles (fft_device.cuh layout) of the n_fft-point transform
+                               // (fused path) or of the n_fft/16-point row transform (large path)
+    const float2* tw_half;     // per-pass twiddles of the n_fft/2-point transform (fused path)
+    const float2* tw_pack;     // [n_fft/4+1]   exp(-2*pi*i*k/n_fft) for the real-signal packing (fused path)
     const float2* tw_col;      // [16][n_fft/16] exp(-2*pi*i*k1*n2/n_fft), large path only
 };
 
