@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libupmix_b200.so")
+LIB_PATH = os.environ.get("UPMIX_B200_LIB") or os.path.join(_HERE, "csrc", "libupmix_b200.so")
 
 OUT_LSCRS = 0
 OUT_FOLD = 1

@@ -102,9 +102,29 @@ __host__ __device__ constexpr int PAD(int i) { return i + (i >> pad_shift(PLAN))
 template <int PLAN>
 __host__ __device__ constexpr int PADSZ() { return fft_size(PLAN) + (fft_size(PLAN) >> pad_shift(PLAN)); }
 
-// One Stockham pass over ROWS rows of N points held in `buf` (row stride PADSZ<N>()).
-//   FIRST: inputs come from ld(row, idx) instead of buf;  LAST: outputs go to st(row, idx, v).
-//   tw: this transform's twiddle table (forward sign; conjugated here for DIR = +1).
+// Output functor of a transform: `pre(row, k)` is called BEFORE the pass barrier and may start global
+// loads the store needs (window samples ...); `put(row, k, value, aux)` is called after the butterfly.
+// Warps issue in order, so anything loaded in `pre` is in flight across the barrier and the butterfly.
+struct NoAux {};
+template <class Pre, class Put>
+struct StoreFn {
+    Pre pre;
+    Put put;
+};
+template <class Pre, class Put>
+__device__ __forceinline__ StoreFn<Pre, Put> make_store(Pre pre, Put put) { return StoreFn<Pre, Put>{pre, put}; }
+template <class Put>
+__device__ __forceinline__ auto make_store(Put put) {
+    auto pre = [](int, int) { return NoAux{}; };
+    return StoreFn<decltype(pre), Put>{pre, put};
+}
+
+// One Stockham pass over ROWS rows of N points held in `buf` (row stride PADSZ<PLAN>()).
+//   FIRST: inputs come from ld(row, idx, it, r) instead of buf (it, r: which of the thread's
+//          butterflies / which input, compile-time after unrolling, so ld may index registers);
+//   LAST:  outputs go to st.put(row, idx, v, aux) with aux = st.pre(row, idx) fetched before the barrier.
+//   tw: this transform's twiddle table (forward sign; conjugated here for DIR = +1); the pass's
+//   twiddles are also fetched before the barrier.
 template <int PLAN, int P, int DIR, int T, int ROWS, bool LD_SMEM, class Ld, class St>
 __device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2* __restrict__ tw, Ld& ld, St& st) {
     constexpr int N = fft_size(PLAN);
@@ -116,16 +136,37 @@ __device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2
     constexpr int TOTAL = NB * ROWS;
     constexpr int IT = (TOTAL + T - 1) / T;
     constexpr int RS = PADSZ<PLAN>();
+    // padded addresses are affine in r whenever the stride is a multiple of the padding period
+    constexpr int PERIOD = 1 << pad_shift(PLAN);
+    constexpr bool LD_LIN = NB % PERIOD == 0;
+    constexpr int LD_STR = NB + NB / PERIOD;
+    constexpr bool ST_LIN = NS % PERIOD == 0 || (NS == 1 && R == PERIOD);
+    constexpr int ST_STR = NS == 1 ? 1 : NS + NS / PERIOD;
     float2 v[IT][R];
+    float2 w[IT][NS > 1 ? R : 1];
+    decltype(st.pre(0, 0)) aux[IT][LAST ? R : 1];
 #pragma unroll
     for (int it = 0; it < IT; it++) {
         const int jj = tid + it * T;
         if (TOTAL % T == 0 || jj < TOTAL) {
             const int row = ROWS == 1 ? 0 : jj / NB;
             const int j = ROWS == 1 ? jj : jj - row * NB;
+            const int k = j & (NS - 1);
+            if (NS > 1) {                          // global loads first: they overlap the barrier
+                const float2* __restrict__ twp = tw + fft_tw_offset(PLAN, P) + k;
+#pragma unroll
+                for (int r = 1; r < R; r++) w[it][r] = __ldg(twp + (r - 1) * NS);
+            }
+            if (LAST) {
+                const int j0 = (j - k) * R + k;
+#pragma unroll
+                for (int r = 0; r < R; r++) aux[it][r] = st.pre(row, j0 + r * NS);
+            }
+            const float2* __restrict__ src = buf + row * RS + PAD<PLAN>(j);
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                if (FIRST) v[it][r] = ld(row, j + r * NB);
+                if (FIRST) v[it][r] = ld(row, j + r * NB, it, r);
+                else if (LD_LIN) v[it][r] = src[r * LD_STR];
                 else v[it][r] = buf[row * RS + PAD<PLAN>(j + r * NB)];
             }
         }
@@ -139,19 +180,20 @@ __device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2
             const int j = ROWS == 1 ? jj : jj - row * NB;
             const int k = j & (NS - 1);
             if (NS > 1) {
-                const float2* __restrict__ twp = tw + fft_tw_offset(PLAN, P) + k;
 #pragma unroll
                 for (int r = 1; r < R; r++) {
-                    float2 w = __ldg(twp + (r - 1) * NS);
-                    if (DIR > 0) w.y = -w.y;
-                    v[it][r] = cmul(v[it][r], w);
+                    float2 ww = w[it][r];
+                    if (DIR > 0) ww.y = -ww.y;
+                    v[it][r] = cmul(v[it][r], ww);
                 }
             }
             Dft<R, DIR>::run(v[it]);
             const int j0 = (j - k) * R + k;
+            float2* __restrict__ dst = buf + row * RS + PAD<PLAN>(j0);
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                if (LAST) st(row, j0 + r * NS, v[it][r]);
+                if (LAST) st.put(row, j0 + r * NS, v[it][r], aux[it][r]);
+                else if (ST_LIN) dst[r * ST_STR] = v[it][r];
                 else buf[row * RS + PAD<PLAN>(j0 + r * NS)] = v[it][r];
             }
         }
@@ -165,8 +207,8 @@ __device__ __forceinline__ void stockham_rec(float2* buf, int tid, const float2*
     if constexpr (P + 1 < fft_num_passes(PLAN)) stockham_rec<PLAN, P + 1, DIR, T, ROWS, LD_SMEM, Ld, St>(buf, tid, tw, ld, st);
 }
 
-// Full transform of ROWS rows of fft_size(PLAN) points.  ld(row, n) supplies input point n; st(row, k,
-// value) receives output point k (natural order).  LD_SMEM says ld reads the same shared buffer
+// Full transform of ROWS rows of fft_size(PLAN) points.  ld(row, n, it, r) supplies input point n; st
+// (a StoreFn) receives output point k (natural order).  LD_SMEM says ld reads the same shared buffer
 // (forces the read barrier).  tw = twiddle table of THIS plan (fft_tw_size(PLAN) entries).  Ends with
 // a __syncthreads().
 template <int PLAN, int DIR, int T, int ROWS, bool LD_SMEM, class Ld, class St>
@@ -178,16 +220,31 @@ __device__ __forceinline__ void fft_smem(float2* buf, int tid, const float2* __r
 // ---------------------------------------------------------------------------------------------
 // Centre mask (reference: center_extraction.py:373-384; bela/upmix.cpp:363-385), float32.
 // coherence = |SL*conj(SR)| / (|SL||SR| + EPS) is evaluated as m / (m + EPS) with m = |SL||SR|
-// (identical in exact arithmetic).
+// (identical in exact arithmetic), balance = (|SL|-|SR|) / (|SL|+|SR|+EPS).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sqrt_approx(float x) {       // MUFU-based, max rel. error 2^-22, sqrt(0) = 0
+    float y;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float div_approx(float a, float b) { // MUFU.RCP-based, 2 ulp, |b| in (2^-126, 2^126)
+    float y;
+    asm("div.approx.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b));
+    return y;
+}
+
+// centerFactor = coherence * (1 - |balance|) = m (s - |d|) / ((m + EPS) s),  m = |SL||SR|, s = |SL|+|SR|+EPS,
+// d = |SL|-|SR|: one division instead of two.  The magnitudes and the quotient use the approximate
+// (2^-22) square root and division: the factor only scales SL+SR, so its relative error (< 1e-6) sits
+// 120 dB below the signal; the denominators are >= 1e-24, far from the approximate divider's limits.
 __device__ __forceinline__ void centre_split(float2 sl, float2 sr, float2& c, float2& ls, float2& rs) {
     constexpr float EPS = 1e-12f;
-    const float ml = sqrtf(sl.x * sl.x + sl.y * sl.y);
-    const float mr = sqrtf(sr.x * sr.x + sr.y * sr.y);
+    const float ml = sqrt_approx(sl.x * sl.x + sl.y * sl.y);
+    const float mr = sqrt_approx(sr.x * sr.x + sr.y * sr.y);
     const float m = ml * mr;
-    const float coh = m / (m + EPS);
-    const float bal = (ml - mr) / (ml + mr + EPS);
-    const float h = 0.5f * (coh * (1.0f - fabsf(bal)));
+    const float sden = ml + mr + EPS;
+    const float cf = div_approx(m * (sden - fabsf(ml - mr)), (m + EPS) * sden);
+    const float h = 0.5f * cf;
     c = make_float2(h * (sl.x + sr.x), h * (sl.y + sr.y));
     ls = csub(sl, c);
     rs = csub(sr, c);

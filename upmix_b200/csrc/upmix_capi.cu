@@ -101,8 +101,10 @@ Layout make_layout(const UpmixPlan* p, int64_t seg_len, int n_tracks) {
     return l;
 }
 
-int pick_hops_per_run(const UpmixPlan* p, int64_t total_hops, int n_tracks) {
-    const int64_t target_ctas = (int64_t)p->sm_count * 4;
+// Hops per CTA of the fused kernel: long runs amortise the (n_fft/hop - 1) warm-up frames, but the
+// grid should fill every SM with a few waves of co-resident CTAs.
+int pick_hops_per_run(const UpmixPlan* p, int n_fft, int64_t total_hops, int n_tracks) {
+    const int64_t target_ctas = (int64_t)p->sm_count * fused_ctas_per_sm(n_fft) * 3;
     int64_t r = (total_hops * n_tracks + target_ctas - 1) / target_ctas;
     return (int)std::min<int64_t>(64, std::max<int64_t>(8, r));
 }
@@ -154,7 +156,7 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
                 a.hops_per_run = (int)total_hops;              // the ring is carried: one CTA per track
                 CU_CHECK(launch_band_fused(b, a, 1, n_tracks, st));
             } else {
-                a.hops_per_run = pick_hops_per_run(p, total_hops, n_tracks);
+                a.hops_per_run = pick_hops_per_run(p, b.n_fft, total_hops, n_tracks);
                 const int n_runs = (int)((total_hops + a.hops_per_run - 1) / a.hops_per_run);
                 CU_CHECK(launch_band_fused(b, a, n_runs, n_tracks, st));
             }

@@ -25,20 +25,48 @@ namespace upmix {
 // Per-size configuration of the fused kernel: radix plans of the N-point and N/2-point transforms,
 // threads per CTA (= per frame in flight) and the CTAs per SM the register budget is sized for.
 template <int N> struct FusedCfg;
+#define UPMIX_FUSED_CFG_X(N_, ...) UPMIX_FUSED_CFG(N_, __VA_ARGS__)
 #define UPMIX_FUSED_CFG(N_, FULL_, HALF_, T_, MINB_)                                                     \
     template <> struct FusedCfg<N_> {                                                                     \
         static constexpr int FULL = FULL_, HALF = HALF_, T = T_, MINB = MINB_;                            \
         static_assert(fft_size(FULL_) == N_ && fft_size(HALF_) == N_ / 2, "plan does not match the size"); \
         static constexpr int SMEM = (PADSZ<FULL_>() + PADSZ<HALF_>()) * (int)sizeof(float2) + 3 * N_ * (int)sizeof(float); \
     };
-UPMIX_FUSED_CFG(64, mkplan(8, 8), mkplan(8, 4), 32, 16)
-UPMIX_FUSED_CFG(128, mkplan(16, 8), mkplan(8, 8), 32, 8)
-UPMIX_FUSED_CFG(256, mkplan(16, 16), mkplan(16, 8), 32, 8)
-UPMIX_FUSED_CFG(512, mkplan(32, 16), mkplan(16, 16), 32, 8)
-UPMIX_FUSED_CFG(1024, mkplan(32, 32), mkplan(32, 16), 32, 8)
-UPMIX_FUSED_CFG(2048, mkplan(16, 16, 8), mkplan(16, 16, 4), 128, 4)
-UPMIX_FUSED_CFG(4096, mkplan(16, 16, 16), mkplan(16, 16, 8), 256, 2)
-UPMIX_FUSED_CFG(8192, mkplan(32, 16, 16), mkplan(16, 16, 16), 256, 1)
+// Chosen by measurement on B200 (profiles/band_bench.py; see profiles/r01_tuning.md): 16-32 points per
+// thread, every lane busy in every pass, a radix-32 first pass from 2048 points up (three passes), and
+// enough registers to avoid spills even if that leaves 8-12 warps per SM.
+#ifndef UPMIX_CFG_64
+#define UPMIX_CFG_64 mkplan(8, 8), mkplan(8, 4), 32, 16
+#endif
+UPMIX_FUSED_CFG_X(64, UPMIX_CFG_64)
+#ifndef UPMIX_CFG_128
+#define UPMIX_CFG_128 mkplan(8, 4, 4), mkplan(4, 4, 4), 32, 16
+#endif
+UPMIX_FUSED_CFG_X(128, UPMIX_CFG_128)
+#ifndef UPMIX_CFG_256
+#define UPMIX_CFG_256 mkplan(8, 8, 4), mkplan(4, 4, 8), 32, 16
+#endif
+UPMIX_FUSED_CFG_X(256, UPMIX_CFG_256)
+#ifndef UPMIX_CFG_512
+#define UPMIX_CFG_512 mkplan(16, 8, 4), mkplan(8, 8, 4), 32, 16
+#endif
+UPMIX_FUSED_CFG_X(512, UPMIX_CFG_512)
+#ifndef UPMIX_CFG_1024
+#define UPMIX_CFG_1024 mkplan(16, 16, 4), mkplan(16, 8, 4), 64, 6
+#endif
+UPMIX_FUSED_CFG_X(1024, UPMIX_CFG_1024)
+#ifndef UPMIX_CFG_2048
+#define UPMIX_CFG_2048 mkplan(32, 8, 8), mkplan(16, 16, 4), 64, 4
+#endif
+UPMIX_FUSED_CFG_X(2048, UPMIX_CFG_2048)
+#ifndef UPMIX_CFG_4096
+#define UPMIX_CFG_4096 mkplan(32, 16, 8), mkplan(16, 16, 8), 128, 2
+#endif
+UPMIX_FUSED_CFG_X(4096, UPMIX_CFG_4096)
+#ifndef UPMIX_CFG_8192
+#define UPMIX_CFG_8192 mkplan(32, 16, 16), mkplan(16, 16, 16), 256, 1
+#endif
+UPMIX_FUSED_CFG_X(8192, UPMIX_CFG_8192)
 
 template <int N>
 __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_kernel(const BandDev b, const SegArgs a) {
@@ -84,89 +112,134 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
     const float2* __restrict__ twh = b.tw_half;
     const float2* __restrict__ twp = b.tw_pack;
 
+    // Input prefetch: the raw samples and window values of the NEXT frame are requested before the
+    // current frame's emit loop and consumed by the next iteration's first FFT pass.  xin[it][r] is
+    // point n = tid + it*T + r*NB0 of the frame, exactly what pass 0 asks for.
+    constexpr int R0 = fft_radix(PF, 0);
+    constexpr int NB0 = N / R0;
+    constexpr int IT0 = (NB0 + T - 1) / T;
+    float2 xin[IT0][R0];
+    float xw[IT0][R0];
+    int lo_n = 0, hi_n = 0;                       // valid frame-local index window of the prefetched frame
+    auto prefetch = [&](long long fr) {
+        const long long s0n = fr * H;
+        lo_n = (int)max(0LL, min((long long)N, a.in_begin - s0n));
+        hi_n = (int)max(0LL, min((long long)N, a.in_end - s0n));
+        const bool any = hi_n > lo_n;
+        const int lo_c = min(lo_n, N - 1);
+        const float* __restrict__ pl = inl + (s0n - a.in_begin);     // pl[n] is sample s0n + n
+        const float* __restrict__ pr = inr + (s0n - a.in_begin);
+#pragma unroll
+        for (int it = 0; it < IT0; it++) {
+            const int j = tid + it * T;
+            if (NB0 % T == 0 || j < NB0) {
+#pragma unroll
+                for (int r = 0; r < R0; r++) {
+                    const int n = j + r * NB0;
+                    const int i = (n >= lo_n && n < hi_n) ? n : lo_c;   // clamped: unconditional loads
+                    xw[it][r] = __ldg(ana + n);
+                    xin[it][r] = any ? make_float2(__ldg(pl + i), __ldg(pr + i)) : make_float2(0.f, 0.f);
+                }
+            }
+        }
+    };
+    prefetch(f_begin);
+
     for (long long f = f_begin; f < h1; ++f) {
         const long long s0 = f * H;
         const int base = (int)(f % K) * H;
 
         // ---- forward: Z = FFT_N( ana * (L + iR) ) -----------------------------------------------
-        // unconditional (clamped) loads so that the whole batch is in flight at once; samples outside
-        // [in_begin, in_end) -- before the track, past its end, or another shard's -- read as zero
-        auto ld_in = [&](int, int n) -> float2 {
-            const long long s = s0 + n;
-            const bool ok = s >= a.in_begin && s < a.in_end;
-            const long long idx = ok ? s - a.in_begin : 0;
-            const float w = __ldg(ana + n);
-            const float l = __ldg(inl + idx), r = __ldg(inr + idx);
-            return ok ? make_float2(l * w, r * w) : make_float2(0.f, 0.f);
+        // samples outside [in_begin, in_end) -- before the track, past its end, or another shard's --
+        // read as zero
+        const int lo_f = lo_n, hi_f = hi_n;
+        auto ld_in = [&](int, int n, int it, int r) -> float2 {
+            const bool ok = n >= lo_f && n < hi_f;
+            const float wn = xw[it][r];
+            return ok ? make_float2(xin[it][r].x * wn, xin[it][r].y * wn) : make_float2(0.f, 0.f);
         };
-        auto st_z = [&](int, int k, float2 v) { Z[PAD<PF>(k)] = v; };
+        auto st_z = make_store([&](int, int k, float2 v, NoAux) { Z[PAD<PF>(k)] = v; });
         fft_smem<PF, -1, T, 1, false>(Z, tid, tw, ld_in, st_z);
 
         // ---- split / gain / mask; Y1 = Ls + i*Rs in place, C packed for the half-size inverse ---
         {
             constexpr int ITM = (M / 2 + 1 + T - 1) / T;
-            float g1[ITM], g2[ITM];
-            float2 wp[ITM];
+            constexpr int CH = 3;                        // iterations whose table loads fly together
+#pragma unroll 1
+            for (int it0 = 0; it0 < ITM; it0 += CH) {
+                float g1[CH], g2[CH];
+                float2 wp[CH];
 #pragma unroll
-            for (int it = 0; it < ITM; it++) {          // table loads first, all in flight together
-                const int k = min(tid + it * T, M / 2);
-                g1[it] = __ldg(gain + k);
-                g2[it] = __ldg(gain + M - k);
-                wp[it] = __ldg(twp + k);
-            }
+                for (int i = 0; i < CH; i++) {
+                    const int k = min(tid + (it0 + i) * T, M / 2);
+                    g1[i] = __ldg(gain + k);
+                    g2[i] = __ldg(gain + M - k);
+                    wp[i] = __ldg(twp + k);
+                }
 #pragma unroll
-            for (int it = 0; it < ITM; it++) {
-                const int k = tid + it * T;
-                if (k > M / 2) break;
-                const int k2 = M - k;
-                const int km = (N - k) & (N - 1);
-                const float2 a1 = Z[PAD<PF>(k)], b1 = Z[PAD<PF>(km)];
-                const float2 a2 = Z[PAD<PF>(k2)], b2 = Z[PAD<PF>(M + k)];
-                float2 c1 = make_float2(0.f, 0.f), l1 = c1, r1 = c1, c2 = c1, l2 = c1, r2 = c1;
-                if (g1[it] != 0.f) split_gain_mask(a1, b1, g1[it], c1, l1, r1);
-                if (g2[it] != 0.f) split_gain_mask(a2, b2, g2[it], c2, l2, r2);
-                Z[PAD<PF>(k)] = make_float2(l1.x - r1.y, l1.y + r1.x);
-                Z[PAD<PF>(km)] = make_float2(l1.x + r1.y, r1.x - l1.y);
-                Z[PAD<PF>(k2)] = make_float2(l2.x - r2.y, l2.y + r2.x);
-                Z[PAD<PF>(M + k)] = make_float2(l2.x + r2.y, r2.x - l2.y);
-                // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);  IFFT_M(z)[m] = c[2m] + i c[2m+1]
-                const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
-                const float2 B = make_float2(c1.x - c2.x, c1.y + c2.y);
-                const float2 D = cmul(B, make_float2(wp[it].x, -wp[it].y));
-                Cz[PAD<PH>(k)] = make_float2(A.x - D.y, A.y + D.x);
-                if (k > 0) Cz[PAD<PH>(M - k)] = make_float2(A.x + D.y, D.x - A.y);
+                for (int i = 0; i < CH; i++) {
+                    const int k = tid + (it0 + i) * T;
+                    if (k <= M / 2) {
+                        const int k2 = M - k;
+                        const int km = (N - k) & (N - 1);
+                        const float2 a1 = Z[PAD<PF>(k)], b1 = Z[PAD<PF>(km)];
+                        const float2 a2 = Z[PAD<PF>(k2)], b2 = Z[PAD<PF>(M + k)];
+                        float2 c1 = make_float2(0.f, 0.f), l1 = c1, r1 = c1, c2 = c1, l2 = c1, r2 = c1;
+                        if (g1[i] != 0.f) split_gain_mask(a1, b1, g1[i], c1, l1, r1);
+                        if (g2[i] != 0.f) split_gain_mask(a2, b2, g2[i], c2, l2, r2);
+                        Z[PAD<PF>(k)] = make_float2(l1.x - r1.y, l1.y + r1.x);
+                        Z[PAD<PF>(km)] = make_float2(l1.x + r1.y, r1.x - l1.y);
+                        Z[PAD<PF>(k2)] = make_float2(l2.x - r2.y, l2.y + r2.x);
+                        Z[PAD<PF>(M + k)] = make_float2(l2.x + r2.y, r2.x - l2.y);
+                        // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);
+                        // IFFT_M(z)[m] = c[2m] + i c[2m+1]
+                        const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
+                        const float2 B = make_float2(c1.x - c2.x, c1.y + c2.y);
+                        const float2 D = cmul(B, make_float2(wp[i].x, -wp[i].y));
+                        Cz[PAD<PH>(k)] = make_float2(A.x - D.y, A.y + D.x);
+                        if (k > 0) Cz[PAD<PH>(M - k)] = make_float2(A.x + D.y, D.x - A.y);
+                    }
+                }
             }
         }
         __syncthreads();
 
         // ---- inverse transforms, synthesis window, overlap-add (oldest frame first) --------------
-        auto ld_z = [&](int, int n) -> float2 { return Z[PAD<PF>(n)]; };
-        auto st_lr = [&](int, int n, float2 v) {
-            const float w = __ldg(syn + n);
-            const int p = (base + n) & (N - 1);
-            ring[N + p] += v.x * w;
-            ring[2 * N + p] += v.y * w;
-        };
+        auto ld_z = [&](int, int n, int, int) -> float2 { return Z[PAD<PF>(n)]; };
+        auto st_lr = make_store([&](int, int n) -> float { return __ldg(syn + n); },
+                                [&](int, int n, float2 v, float wn) {
+                                    const int p = (base + n) & (N - 1);
+                                    ring[N + p] += v.x * wn;
+                                    ring[2 * N + p] += v.y * wn;
+                                });
         fft_smem<PF, +1, T, 1, true>(Z, tid, tw, ld_z, st_lr);
-        auto ld_c = [&](int, int n) -> float2 { return Cz[PAD<PH>(n)]; };
-        auto st_c = [&](int, int m, float2 v) {
-            const int n = 2 * m;
-            const int p = (base + n) & (N - 1);
-            ring[p] += v.x * __ldg(syn + n);
-            ring[p + 1] += v.y * __ldg(syn + n + 1);
-        };
+        auto ld_c = [&](int, int n, int, int) -> float2 { return Cz[PAD<PH>(n)]; };
+        auto st_c = make_store([&](int, int m) -> float2 { return __ldg(reinterpret_cast<const float2*>(syn) + m); },
+                               [&](int, int m, float2 v, float2 wn) {
+                                   const int p = (base + 2 * m) & (N - 1);
+                                   float2* q = reinterpret_cast<float2*>(ring + p);
+                                   float2 acc = *q;
+                                   acc.x += v.x * wn.x;
+                                   acc.y += v.y * wn.y;
+                                   *q = acc;
+                               });
         fft_smem<PH, +1, T, 1, true>(Cz, tid, twh, ld_c, st_c);
+
+        // ---- request the next frame's input, then emit --------------------------------------------
+        if (f + 1 < h1) prefetch(f + 1);
 
         // ---- emit the hop this frame finished, clear its ring slots --------------------------------
         const bool emit = f >= h0;
-        for (int i = tid; i < H; i += T) {
-            const long long s = s0 + i;
-            const bool wr = emit && s >= a.seg_begin && s < a.seg_end;
+        const int e_lo = (int)max(0LL, min((long long)H, a.seg_begin - s0));
+        const int e_hi = emit ? (int)max(0LL, min((long long)H, a.seg_end - s0)) : 0;
 #pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                const float v = ring[ch * N + base + i];
-                ring[ch * N + base + i] = 0.f;
-                if (wr) outp[ch][s - a.out_begin] = v;
+        for (int ch = 0; ch < 3; ch++) {
+            float* __restrict__ po = outp[ch] + (s0 - a.out_begin);
+            float* rg = ring + ch * N + base;
+            for (int i = tid; i < H; i += T) {
+                const float v = rg[i];
+                rg[i] = 0.f;
+                if (i >= e_lo && i < e_hi) po[i] = v;
             }
         }
         __syncthreads();
@@ -251,12 +324,12 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
     // forward row transforms: rows (f0,ka) (f0,kb) then (f1,ka) (f1,kb)
 #pragma unroll
     for (int g = 0; g < 2; g++) {
-        auto ld = [&](int row, int n) -> float2 {
+        auto ld = [&](int row, int n, int, int) -> float2 {
             const int k1 = row ? kb : ka;
             return A[(fbase + (long long)g * COL_R + k1) * N2 + n];
         };
         float2* buf = S + 2 * g * RS;
-        auto st = [&](int row, int k, float2 v) { buf[row * RS + PAD<PL>(k)] = v; };
+        auto st = make_store([&](int row, int k, float2 v, NoAux) { buf[row * RS + PAD<PL>(k)] = v; });
         fft_smem<PL, -1, T, 2, false>(buf, tid, tw, ld, st);
     }
 
@@ -310,13 +383,13 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 #pragma unroll
     for (int g = 0; g < 3; g++) {
         float2* buf = S + 2 * g * RS;
-        auto ld = [&](int row, int n) -> float2 { return buf[row * RS + PAD<PL>(n)]; };
+        auto ld = [&](int row, int n, int, int) -> float2 { return buf[row * RS + PAD<PL>(n)]; };
         float2* dst = g < 2 ? w.b1 + (fbase + (long long)g * COL_R) * N2
                             : w.b2 + (((long long)track * (w.n_frames / 2) + fp) * COL_R) * N2;
-        auto st = [&](int row, int n, float2 v) {
+        auto st = make_store([&](int row, int n, float2 v, NoAux) {
             const int k1 = row ? kb : ka;
             dst[(long long)k1 * N2 + n] = v;
-        };
+        });
         fft_smem<PL, +1, T, 2, true>(buf, tid, tw, ld, st);
     }
     (void)N;
@@ -518,6 +591,15 @@ void fused_plans(int n_fft, int* full, int* half) {
         UPMIX_CASE(4096) UPMIX_CASE(8192)
 #undef UPMIX_CASE
         default: break;
+    }
+}
+int fused_ctas_per_sm(int n_fft) {
+    switch (n_fft) {
+#define UPMIX_CASE(N_) case N_: return FusedCfg<N_>::MINB;
+        UPMIX_CASE(64) UPMIX_CASE(128) UPMIX_CASE(256) UPMIX_CASE(512) UPMIX_CASE(1024) UPMIX_CASE(2048)
+        UPMIX_CASE(4096) UPMIX_CASE(8192)
+#undef UPMIX_CASE
+        default: return 1;
     }
 }
 int row_plan(int n2) {
