@@ -217,11 +217,15 @@ class Plan:
     def stream_open(self, n_tracks: int = 1):
         return Stream(self, n_tracks)
 
-    # -- host tensors (pinned staging) -------------------------------------------------------------
-    def process_host_tensors(self, L, R):
-        """L, R: float32 CPU torch tensors [n] (pinned memory makes the copies asynchronous).  Copies
-        them to the device, processes, copies the outputs into (cached) pinned host tensors and
-        waits.  Returns CPU tensors; they are overwritten by the next call on this plan."""
+    # -- host tensors (pinned staging), pipelined over time segments ---------------------------------
+    def process_host_tensors(self, L, R, segment_seconds: float = 0.0, sample_rate: float = 48000.0):
+        """L, R: float32 CPU torch tensors [n] (pinned memory makes the copies asynchronous).  The
+        track is cut into time segments (multiples of the largest hop); input chunks go up on one
+        stream, each segment is processed as soon as its halo'd input has landed
+        (upmix_process_segment: bit-identical to one whole-track call) and its outputs come down on a
+        third stream, so H2D, kernels and D2H overlap.  segment_seconds = 0 picks up to 8 segments of
+        at least two minutes (short segments under-fill the GPU).  Returns pinned CPU tensors,
+        overwritten by the next call on this plan."""
         torch = _torch()
         if L.dtype != torch.float32 or R.dtype != torch.float32 or L.dim() != 1 or L.shape != R.shape:
             raise TypeError("L and R must be 1-D float32 CPU tensors of equal length")
@@ -231,14 +235,52 @@ class Plan:
         cache = getattr(self, "_host_cache", None)
         if cache is None or cache[0] != n:
             self._host_cache = cache = (n, torch.empty((2, n), dtype=torch.float32, device=dev),
-                                        torch.empty((n_out, 1, n), dtype=torch.float32, device=dev),
-                                        torch.empty((n_out, n), dtype=torch.float32, pin_memory=True))
-        _, d_in, d_out, h_out = cache
-        d_in[0].copy_(L, non_blocking=True)
-        d_in[1].copy_(R, non_blocking=True)
-        self.process_segment(d_in[0:1], d_in[1:2], 0, n, 0, n, out=d_out)
-        h_out.copy_(d_out[:, 0], non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+                                        torch.empty((n_out, n), dtype=torch.float32, device=dev),
+                                        torch.empty((n_out, n), dtype=torch.float32, pin_memory=True),
+                                        torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        _, d_in, d_out, h_out, s_up, s_down = cache
+        main = torch.cuda.current_stream(dev)
+        align = max(self.hops)
+        if segment_seconds <= 0:
+            n_seg = max(1, min(8, int(n / (120.0 * sample_rate))))
+            seg = -(-n // n_seg)
+        else:
+            seg = int(segment_seconds * sample_rate)
+        seg = max(align, -(-seg // align) * align)
+        bounds = list(range(0, n, seg)) + [n]
+        # input chunks: chunk i carries samples [bounds[i], bounds[i+1]); segment i needs chunks up to
+        # the one holding sample min(n, bounds[i+1] + halo) - 1
+        s_up.wait_stream(main)
+        s_down.wait_stream(main)
+        up_done = []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            with torch.cuda.stream(s_up):
+                d_in[0, a:b].copy_(L[a:b], non_blocking=True)
+                d_in[1, a:b].copy_(R[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_up)
+            up_done.append(ev)
+        wsb = self.workspace_bytes(seg, 1)
+        ws = self._workspace(wsb)
+        import bisect
+        for i, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+            need = min(n, b + self.halo) - 1
+            last_chunk = min(len(up_done) - 1, bisect.bisect_right(bounds, need) - 1)
+            main.wait_event(up_done[last_chunk])
+            oc, ol, orr = (d_out[0, a:b], d_out[1, a:b], d_out[2, a:b]) if n_out == 3 else (None, d_out[0, a:b], d_out[1, a:b])
+            with torch.cuda.device(dev):
+                _check(self._lib.upmix_process_segment(
+                    self._h, d_in[0].data_ptr(), d_in[1].data_ptr(), 0, n, n, a, b, 1, n,
+                    oc.data_ptr() if oc is not None else None, ol.data_ptr(), orr.data_ptr(), n,
+                    ws.data_ptr(), wsb, main.cuda_stream))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(s_down):
+                s_down.wait_event(ev)
+                for ch in range(n_out):
+                    h_out[ch, a:b].copy_(d_out[ch, a:b], non_blocking=True)
+        main.wait_stream(s_down)
+        main.synchronize()
         return tuple(h_out[i] for i in range(n_out))
 
     # -- host buffers ----------------------------------------------------------------------------
