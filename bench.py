@@ -186,6 +186,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout; keep it to the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     import upmix_b200.center_extraction as ce

@@ -52,7 +52,7 @@ struct DeviceGuard {
     }
 };
 
-constexpr int K3_HOPS_PER_RUN = 8;
+constexpr int K3_HOPS_PER_RUN = 16;
 
 }  // namespace
 

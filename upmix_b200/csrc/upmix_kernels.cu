@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
 // large-N path, N = 16 * N2
 // ---------------------------------------------------------------------------------------------
 // K1: one thread per (frame, column n2): windowed samples x[16 rows][n2] -> radix-16 DFT over the
-// rows -> twiddle W_N^{n2*k1} -> A[frame][k1][n2].
+// rows -> A[frame][k1][n2] (the four-step twiddle W_N^{n2*k1} is applied by the row kernel's loads).
 __global__ void __launch_bounds__(128) col_fwd_kernel(const BandDev b, const SegArgs a, const WaveArgs w) {
     const int N2 = b.n_fft / COL_R;
     const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,9 +282,8 @@ __global__ void __launch_bounds__(128) col_fwd_kernel(const BandDev b, const Seg
     }
     Dft<COL_R, -1>::run(v);
     float2* dst = w.a + (((long long)track * w.n_frames + fl) * COL_R) * N2 + n2;
-    dst[0] = v[0];
 #pragma unroll
-    for (int k1 = 1; k1 < COL_R; k1++) dst[(long long)k1 * N2] = cmul(v[k1], __ldg(b.tw_col + k1 * N2 + n2));
+    for (int k1 = 0; k1 < COL_R; k1++) dst[(long long)k1 * N2] = v[k1];     // twiddled by the row kernel
 }
 
 template <int N2> struct RowCfg;
@@ -295,9 +294,18 @@ template <int N2> struct RowCfg;
         static constexpr int T = 2 * N2_ / fft_radix(PLAN_, 0); /* two rows, one butterfly each */ \
         static constexpr int SMEM = 6 * PADSZ<PLAN_>() * (int)sizeof(float2);                     \
     };
-UPMIX_ROW_CFG(1024, mkplan(16, 16, 4))
-UPMIX_ROW_CFG(2048, mkplan(16, 16, 8))
-UPMIX_ROW_CFG(4096, mkplan(16, 16, 16))
+#ifndef UPMIX_ROWPLAN_1024
+#define UPMIX_ROWPLAN_1024 mkplan(16, 16, 4)
+#endif
+#ifndef UPMIX_ROWPLAN_2048
+#define UPMIX_ROWPLAN_2048 mkplan(16, 16, 8)
+#endif
+#ifndef UPMIX_ROWPLAN_4096
+#define UPMIX_ROWPLAN_4096 mkplan(16, 16, 16)
+#endif
+UPMIX_ROW_CFG(1024, UPMIX_ROWPLAN_1024)
+UPMIX_ROW_CFG(2048, UPMIX_ROWPLAN_2048)
+UPMIX_ROW_CFG(4096, UPMIX_ROWPLAN_4096)
 
 // K2: one CTA per (row pair, frame pair, track).  Rows k1 and 16-k1 of the frame's spectrum are
 // mirror images of each other (bin k <-> N-k), so the CTA holds both rows of both frames, finishes
@@ -319,14 +327,15 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
     const long long fbase = ((long long)track * w.n_frames + 2 * fp) * COL_R;
     const float2* __restrict__ A = w.a;
     const float2* __restrict__ tw = b.tw_fft;
+    const float2* __restrict__ twc = b.tw_col;
     const float* __restrict__ gain = b.gain;
 
     // forward row transforms: rows (f0,ka) (f0,kb) then (f1,ka) (f1,kb)
 #pragma unroll
     for (int g = 0; g < 2; g++) {
-        auto ld = [&](int row, int n, int, int) -> float2 {
+        auto ld = [&](int row, int n, int, int) -> float2 {      // A * W_N^{k1 n}: the four-step twiddle
             const int k1 = row ? kb : ka;
-            return A[(fbase + (long long)g * COL_R + k1) * N2 + n];
+            return cmul(A[(fbase + (long long)g * COL_R + k1) * N2 + n], __ldg(twc + k1 * N2 + n));
         };
         float2* buf = S + 2 * g * RS;
         auto st = make_store([&](int row, int k, float2 v, NoAux) { buf[row * RS + PAD<PL>(k)] = v; });
@@ -386,10 +395,11 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
         auto ld = [&](int row, int n, int, int) -> float2 { return buf[row * RS + PAD<PL>(n)]; };
         float2* dst = g < 2 ? w.b1 + (fbase + (long long)g * COL_R) * N2
                             : w.b2 + (((long long)track * (w.n_frames / 2) + fp) * COL_R) * N2;
-        auto st = make_store([&](int row, int n, float2 v, NoAux) {
-            const int k1 = row ? kb : ka;
-            dst[(long long)k1 * N2 + n] = v;
-        });
+        auto st = make_store([&](int row, int n) -> float2 { return __ldg(twc + (row ? kb : ka) * N2 + n); },
+                             [&](int row, int n, float2 v, float2 t) {     // * conj W_N^{k1 n}
+                                 const int k1 = row ? kb : ka;
+                                 dst[(long long)k1 * N2 + n] = cmul(v, make_float2(t.x, -t.y));
+                             });
         fft_smem<PL, +1, T, 2, true>(buf, tid, tw, ld, st);
     }
     (void)N;
@@ -399,7 +409,7 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 // frames before it whose tails reach into the run) the thread finishes the inverse transform down
 // its column (radix-16), applies the synthesis window and overlap-adds in registers: a frame shifts
 // the 16-row accumulator by 4 rows (hop = N/4 = 4*N2), the 4 rows that fall out are finished samples.
-__global__ void __launch_bounds__(128) col_inv_ola_kernel(const BandDev b, const SegArgs a, const WaveArgs w) {
+__global__ void __launch_bounds__(128, 4) col_inv_ola_kernel(const BandDev b, const SegArgs a, const WaveArgs w) {
     const int N2 = b.n_fft / COL_R;
     const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
     if (n2 >= N2) return;
@@ -411,8 +421,7 @@ __global__ void __launch_bounds__(128) col_inv_ola_kernel(const BandDev b, const
     const long long f_begin = max(0LL, h0 - 3);
     float* outp[3] = {a.out_c + (long long)track * a.out_stride, a.out_l + (long long)track * a.out_stride,
                       a.out_r + (long long)track * a.out_stride};
-    const float* __restrict__ syn = b.syn;
-    const float2* __restrict__ twc = b.tw_col;
+    const float* __restrict__ syn = b.syn + n2;
 
     float acc[3][COL_R];
 #pragma unroll
@@ -420,52 +429,59 @@ __global__ void __launch_bounds__(128) col_inv_ola_kernel(const BandDev b, const
 #pragma unroll
         for (int i = 0; i < COL_R; i++) acc[ch][i] = 0.f;
 
+    // finished rows of frame f leave the accumulator; the rest moves up by one hop
+    auto emit_shift = [&](long long f) {
+        const bool emit = f >= h0 && f < h1;
+        const long long s0 = f * H + n2;
+#pragma unroll
+        for (int n1 = 0; n1 < COL_R / 4; n1++) {
+            const long long s = s0 + n1 * N2;
+            if (emit && s >= a.seg_begin && s < a.seg_end) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) outp[ch][s - a.out_begin] = acc[ch][n1];
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+#pragma unroll
+            for (int i = 0; i < COL_R - COL_R / 4; i++) acc[ch][i] = acc[ch][i + COL_R / 4];
+#pragma unroll
+            for (int i = COL_R - COL_R / 4; i < COL_R; i++) acc[ch][i] = 0.f;
+        }
+    };
+
     for (long long p = f_begin >> 1; 2 * p < h1; ++p) {
         const long long fl = 2 * p - w.frame0;              // local index of the even frame
         const float2* __restrict__ B2 = w.b2 + (((long long)track * (w.n_frames / 2) + (fl >> 1)) * COL_R) * N2 + n2;
-        float2 cc[COL_R];
-        cc[0] = B2[0];
+        const float2* __restrict__ B1 = w.b1 + (((long long)track * w.n_frames + fl) * COL_R) * N2 + n2;
+        float wn[COL_R];
+        float codd[COL_R];
 #pragma unroll
-        for (int k1 = 1; k1 < COL_R; k1++) {
-            const float2 t = __ldg(twc + k1 * N2 + n2);
-            cc[k1] = cmul(B2[(long long)k1 * N2], make_float2(t.x, -t.y));
+        for (int n1 = 0; n1 < COL_R; n1++) wn[n1] = __ldg(syn + n1 * N2);
+        {
+            float2 v[COL_R];
+#pragma unroll
+            for (int k1 = 0; k1 < COL_R; k1++) v[k1] = B2[(long long)k1 * N2];
+            Dft<COL_R, +1>::run(v);                          // v[n1] = (c_even[n], c_odd[n]), n = n1*N2 + n2
+#pragma unroll
+            for (int n1 = 0; n1 < COL_R; n1++) {
+                acc[0][n1] += v[n1].x * wn[n1];
+                codd[n1] = v[n1].y;
+            }
         }
-        Dft<COL_R, +1>::run(cc);                            // cc[n1] = (c_even[n], c_odd[n]), n = n1*N2 + n2
 #pragma unroll
         for (int half = 0; half < 2; half++) {
-            const long long f = 2 * p + half;
-            const float2* __restrict__ B1 = w.b1 + (((long long)track * w.n_frames + fl + half) * COL_R) * N2 + n2;
             float2 v[COL_R];
-            v[0] = B1[0];
 #pragma unroll
-            for (int k1 = 1; k1 < COL_R; k1++) {
-                const float2 t = __ldg(twc + k1 * N2 + n2);
-                v[k1] = cmul(B1[(long long)k1 * N2], make_float2(t.x, -t.y));
-            }
+            for (int k1 = 0; k1 < COL_R; k1++) v[k1] = B1[((long long)half * COL_R + k1) * N2];
             Dft<COL_R, +1>::run(v);
 #pragma unroll
             for (int n1 = 0; n1 < COL_R; n1++) {
-                const float wn = __ldg(syn + n1 * N2 + n2);
-                acc[0][n1] += (half ? cc[n1].y : cc[n1].x) * wn;
-                acc[1][n1] += v[n1].x * wn;
-                acc[2][n1] += v[n1].y * wn;
+                if (half) acc[0][n1] += codd[n1] * wn[n1];
+                acc[1][n1] += v[n1].x * wn[n1];
+                acc[2][n1] += v[n1].y * wn[n1];
             }
-            const bool emit = f >= h0 && f < h1;
-#pragma unroll
-            for (int n1 = 0; n1 < COL_R / 4; n1++) {
-                const long long s = f * H + n1 * N2 + n2;
-                if (emit && s >= a.seg_begin && s < a.seg_end) {
-#pragma unroll
-                    for (int ch = 0; ch < 3; ch++) outp[ch][s - a.out_begin] = acc[ch][n1];
-                }
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-#pragma unroll
-                for (int i = 0; i < COL_R - COL_R / 4; i++) acc[ch][i] = acc[ch][i + COL_R / 4];
-#pragma unroll
-                for (int i = COL_R - COL_R / 4; i < COL_R; i++) acc[ch][i] = 0.f;
-            }
+            emit_shift(2 * p + half);
         }
     }
 }
