@@ -233,29 +233,30 @@ __device__ __forceinline__ float div_approx(float a, float b) { // MUFU.RCP-base
     return y;
 }
 
-// centerFactor = coherence * (1 - |balance|) = m (s - |d|) / ((m + EPS) s),  m = |SL||SR|, s = |SL|+|SR|+EPS,
-// d = |SL|-|SR|: one division instead of two.  The magnitudes and the quotient use the approximate
-// (2^-22) square root and division: the factor only scales SL+SR, so its relative error (< 1e-6) sits
-// 120 dB below the signal; the denominators are >= 1e-24, far from the approximate divider's limits.
-__device__ __forceinline__ void centre_split(float2 sl, float2 sr, float2& c, float2& ls, float2& rs) {
+// One bin of the frame: a = Z[k], b = Z[N-k] of the packed transform Z = FFT(l + i r).  With
+// P = a + conj b and Q = a - conj b the two real-signal spectra are SL = P/2, SR = -i Q/2; after the band
+// gain g:  |SL| = g|P|/2, |SR| = g|Q|/2, SL + SR = (g/2)(P.x + Q.y, P.y - Q.x).
+//   centerFactor = coherence (1 - |balance|) = m (s - |d|) / ((m + EPS) s),
+//   m = |SL||SR|, s = |SL| + |SR| + EPS, d = |SL| - |SR|           (one division instead of two)
+//   C = 0.5 centerFactor (SL + SR)
+// and, because SL + i SR = g a and conj SL + i conj SR = g b, the packed spectrum of Ls + i Rs is
+//   Y[k] = g a - (1+i) C,   Y[N-k] = g b - (1+i) conj C            (Ls = SL - C, Rs = SR - C).
+// The magnitudes and the quotient use the approximate (2^-22) square root and division: the factor only
+// scales SL + SR, so its relative error (< 1e-6) sits 120 dB below the signal; the denominator is >= 1e-24,
+// far from the approximate divider's limits.
+__device__ __forceinline__ void mask_bin(float2 a, float2 b, float g, float2& y_lo, float2& y_hi, float2& c) {
     constexpr float EPS = 1e-12f;
-    const float ml = sqrt_approx(sl.x * sl.x + sl.y * sl.y);
-    const float mr = sqrt_approx(sr.x * sr.x + sr.y * sr.y);
+    const float px = a.x + b.x, py = a.y - b.y, qx = a.x - b.x, qy = a.y + b.y;
+    const float hg = 0.5f * g;
+    const float ml = hg * sqrt_approx(px * px + py * py);
+    const float mr = hg * sqrt_approx(qx * qx + qy * qy);
     const float m = ml * mr;
     const float sden = ml + mr + EPS;
     const float cf = div_approx(m * (sden - fabsf(ml - mr)), (m + EPS) * sden);
-    const float h = 0.5f * cf;
-    c = make_float2(h * (sl.x + sr.x), h * (sl.y + sr.y));
-    ls = csub(sl, c);
-    rs = csub(sr, c);
-}
-
-// Split the spectrum of z = l + i*r at bin k (a = Z[k], b = Z[N-k]) into the two real-signal spectra,
-// apply the band gain, run the mask.
-__device__ __forceinline__ void split_gain_mask(float2 a, float2 b, float g, float2& c, float2& ls, float2& rs) {
-    const float2 sl = make_float2(g * (0.5f * (a.x + b.x)), g * (0.5f * (a.y - b.y)));
-    const float2 sr = make_float2(g * (0.5f * (a.y + b.y)), g * (0.5f * (b.x - a.x)));
-    centre_split(sl, sr, c, ls, rs);
+    const float t = (0.5f * cf) * hg;
+    c = make_float2(t * (px + qy), t * (py - qx));
+    y_lo = make_float2(g * a.x - c.x + c.y, g * a.y - c.x - c.y);
+    y_hi = make_float2(g * b.x - c.x - c.y, g * b.y - c.x + c.y);
 }
 
 }  // namespace upmix

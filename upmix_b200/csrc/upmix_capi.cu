@@ -222,7 +222,7 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
             return fail(UPMIX_E_UNSUPPORTED, "band %d: hop=%d must be even and divide n_fft=%d", i, d.hop, d.n_fft);
         if (d.n_fft > FUSED_MAX_N && d.hop * 4 != d.n_fft)
             return fail(UPMIX_E_UNSUPPORTED, "band %d: n_fft=%d > %d requires hop = n_fft/4 (75%% overlap), got %d", i, d.n_fft, FUSED_MAX_N, d.hop);
-        floats += round_up(d.n_fft, 64) * 2 + round_up(d.n_fft / 2 + 1, 64);
+        floats += round_up(d.n_fft + 1, 64) + round_up(d.n_fft, 64) + round_up(d.n_fft / 2 + 1, 64);
         if (d.n_fft > FUSED_MAX_N) {
             floats += 2LL * d.n_fft + round_up(2LL * fft_tw_size(row_plan(d.n_fft / COL_R)), 64);
         } else {
@@ -266,9 +266,9 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
         b.n_fft = d.n_fft;
         b.hop = d.hop;
         b.tw_fft = b.tw_half = b.tw_pack = b.tw_col = nullptr;
-        memcpy(&host[off], d.ana, sizeof(float) * d.n_fft);
+        memcpy(&host[off], d.ana, sizeof(float) * d.n_fft);      // ana[n_fft] = 0 follows (host is zero-filled)
         b.ana = dbase + off;
-        off += round_up(d.n_fft, 64);
+        off += round_up(d.n_fft + 1, 64);
         const float inv_n = 1.0f / (float)d.n_fft;   // exact: n_fft is a power of two
         for (int n = 0; n < d.n_fft; n++) host[off + n] = d.syn[n] * inv_n;
         b.syn = dbase + off;

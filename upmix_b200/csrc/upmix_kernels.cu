@@ -120,25 +120,42 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
     constexpr int IT0 = (NB0 + T - 1) / T;
     float2 xin[IT0][R0];
     float xw[IT0][R0];
-    int lo_n = 0, hi_n = 0;                       // valid frame-local index window of the prefetched frame
     auto prefetch = [&](long long fr) {
         const long long s0n = fr * H;
-        lo_n = (int)max(0LL, min((long long)N, a.in_begin - s0n));
-        hi_n = (int)max(0LL, min((long long)N, a.in_end - s0n));
-        const bool any = hi_n > lo_n;
-        const int lo_c = min(lo_n, N - 1);
         const float* __restrict__ pl = inl + (s0n - a.in_begin);     // pl[n] is sample s0n + n
         const float* __restrict__ pr = inr + (s0n - a.in_begin);
+        if (s0n >= a.in_begin && s0n + N <= a.in_end) {              // whole frame available (CTA-uniform)
 #pragma unroll
-        for (int it = 0; it < IT0; it++) {
-            const int j = tid + it * T;
-            if (NB0 % T == 0 || j < NB0) {
+            for (int it = 0; it < IT0; it++) {
+                const int j = tid + it * T;
+                if (NB0 % T == 0 || j < NB0) {
 #pragma unroll
-                for (int r = 0; r < R0; r++) {
-                    const int n = j + r * NB0;
-                    const int i = (n >= lo_n && n < hi_n) ? n : lo_c;   // clamped: unconditional loads
-                    xw[it][r] = __ldg(ana + n);
-                    xin[it][r] = any ? make_float2(__ldg(pl + i), __ldg(pr + i)) : make_float2(0.f, 0.f);
+                    for (int r = 0; r < R0; r++) {
+                        xw[it][r] = __ldg(ana + j + r * NB0);
+                        xin[it][r] = make_float2(__ldg(pl + j + r * NB0), __ldg(pr + j + r * NB0));
+                    }
+                }
+            }
+        } else {
+            // Samples outside [in_begin, in_end) -- before the track, past its end, or another shard's --
+            // read as zero: their loads are clamped to a valid sample and their window value is taken
+            // from the zero stored after the table (ana[N] == 0), so the loads stay unconditional.
+            const int lo_n = (int)max(0LL, min((long long)N, a.in_begin - s0n));
+            const int hi_n = (int)max(0LL, min((long long)N, a.in_end - s0n));
+            const bool any = hi_n > lo_n;
+            const int lo_c = min(lo_n, N - 1);
+#pragma unroll 1
+            for (int it = 0; it < IT0; it++) {
+                const int j = tid + it * T;
+                if (NB0 % T == 0 || j < NB0) {
+#pragma unroll
+                    for (int r = 0; r < R0; r++) {
+                        const int n = j + r * NB0;
+                        const bool ok = n >= lo_n && n < hi_n;
+                        xw[it][r] = __ldg(ana + (ok ? n : N));
+                        xin[it][r] = any ? make_float2(__ldg(pl + (ok ? n : lo_c)), __ldg(pr + (ok ? n : lo_c)))
+                                         : make_float2(0.f, 0.f);
+                    }
                 }
             }
         }
@@ -150,13 +167,9 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
         const int base = (int)(f % K) * H;
 
         // ---- forward: Z = FFT_N( ana * (L + iR) ) -----------------------------------------------
-        // samples outside [in_begin, in_end) -- before the track, past its end, or another shard's --
-        // read as zero
-        const int lo_f = lo_n, hi_f = hi_n;
-        auto ld_in = [&](int, int n, int it, int r) -> float2 {
-            const bool ok = n >= lo_f && n < hi_f;
+        auto ld_in = [&](int, int, int it, int r) -> float2 {
             const float wn = xw[it][r];
-            return ok ? make_float2(xin[it][r].x * wn, xin[it][r].y * wn) : make_float2(0.f, 0.f);
+            return make_float2(xin[it][r].x * wn, xin[it][r].y * wn);
         };
         auto st_z = make_store([&](int, int k, float2 v, NoAux) { Z[PAD<PF>(k)] = v; });
         fft_smem<PF, -1, T, 1, false>(Z, tid, tw, ld_in, st_z);
@@ -184,13 +197,13 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
                         const int km = (N - k) & (N - 1);
                         const float2 a1 = Z[PAD<PF>(k)], b1 = Z[PAD<PF>(km)];
                         const float2 a2 = Z[PAD<PF>(k2)], b2 = Z[PAD<PF>(M + k)];
-                        float2 c1 = make_float2(0.f, 0.f), l1 = c1, r1 = c1, c2 = c1, l2 = c1, r2 = c1;
-                        if (g1[i] != 0.f) split_gain_mask(a1, b1, g1[i], c1, l1, r1);
-                        if (g2[i] != 0.f) split_gain_mask(a2, b2, g2[i], c2, l2, r2);
-                        Z[PAD<PF>(k)] = make_float2(l1.x - r1.y, l1.y + r1.x);
-                        Z[PAD<PF>(km)] = make_float2(l1.x + r1.y, r1.x - l1.y);
-                        Z[PAD<PF>(k2)] = make_float2(l2.x - r2.y, l2.y + r2.x);
-                        Z[PAD<PF>(M + k)] = make_float2(l2.x + r2.y, r2.x - l2.y);
+                        float2 c1 = make_float2(0.f, 0.f), y1 = c1, y1m = c1, c2 = c1, y2 = c1, y2m = c1;
+                        if (g1[i] != 0.f) mask_bin(a1, b1, g1[i], y1, y1m, c1);
+                        if (g2[i] != 0.f) mask_bin(a2, b2, g2[i], y2, y2m, c2);
+                        Z[PAD<PF>(k)] = y1;
+                        Z[PAD<PF>(km)] = y1m;
+                        Z[PAD<PF>(k2)] = y2;
+                        Z[PAD<PF>(M + k)] = y2m;
                         // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);
                         // IFFT_M(z)[m] = c[2m] + i c[2m+1]
                         const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
@@ -232,14 +245,23 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
         const bool emit = f >= h0;
         const int e_lo = (int)max(0LL, min((long long)H, a.seg_begin - s0));
         const int e_hi = emit ? (int)max(0LL, min((long long)H, a.seg_end - s0)) : 0;
+        const bool whole = e_lo == 0 && e_hi == H && (H % 4 == 0);
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
             float* __restrict__ po = outp[ch] + (s0 - a.out_begin);
             float* rg = ring + ch * N + base;
-            for (int i = tid; i < H; i += T) {
-                const float v = rg[i];
-                rg[i] = 0.f;
-                if (i >= e_lo && i < e_hi) po[i] = v;
+            if (whole && (reinterpret_cast<uintptr_t>(po) & 15) == 0) {      // CTA-uniform: vector copy-out
+                for (int i = tid * 4; i < H; i += T * 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(rg + i);
+                    *reinterpret_cast<float4*>(rg + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    __stcs(reinterpret_cast<float4*>(po + i), v);
+                }
+            } else {
+                for (int i = tid; i < H; i += T) {
+                    const float v = rg[i];
+                    rg[i] = 0.f;
+                    if (i >= e_lo && i < e_hi) po[i] = v;
+                }
             }
         }
         __syncthreads();
@@ -270,15 +292,26 @@ __global__ void __launch_bounds__(128) col_fwd_kernel(const BandDev b, const Seg
     const float* __restrict__ inl = a.in_l + (long long)track * a.in_stride;
     const float* __restrict__ inr = a.in_r + (long long)track * a.in_stride;
     float2 v[COL_R];
+    const float* __restrict__ pl = inl + (s0 - a.in_begin);
+    const float* __restrict__ pr = inr + (s0 - a.in_begin);
+    if (s0 >= a.in_begin && s0 + b.n_fft <= a.in_end) {          // whole frame available (block-uniform)
 #pragma unroll
-    for (int r = 0; r < COL_R; r++) {
-        const int n = r * N2 + n2;
-        const long long s = s0 + n;
-        const bool ok = s >= a.in_begin && s < a.in_end;
-        const long long idx = ok ? s - a.in_begin : 0;
-        const float wn = __ldg(b.ana + n);
-        const float l = __ldg(inl + idx), rr = __ldg(inr + idx);
-        v[r] = ok ? make_float2(l * wn, rr * wn) : make_float2(0.f, 0.f);
+        for (int r = 0; r < COL_R; r++) {
+            const int n = r * N2 + n2;
+            const float wn = __ldg(b.ana + n);
+            v[r] = make_float2(__ldg(pl + n) * wn, __ldg(pr + n) * wn);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < COL_R; r++) {
+            const int n = r * N2 + n2;
+            const long long s = s0 + n;
+            const bool ok = s >= a.in_begin && s < a.in_end;
+            const long long idx = ok ? s - a.in_begin : 0;
+            const float wn = __ldg(b.ana + n);
+            const float l = __ldg(inl + idx), rr = __ldg(inr + idx);
+            v[r] = ok ? make_float2(l * wn, rr * wn) : make_float2(0.f, 0.f);
+        }
     }
     Dft<COL_R, -1>::run(v);
     float2* dst = w.a + (((long long)track * w.n_frames + fl) * COL_R) * N2 + n2;
@@ -375,11 +408,11 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 #pragma unroll
             for (int fr = 0; fr < 2; fr++) {
                 float2* buf = S + 2 * fr * RS;
-                float2 ls = make_float2(0.f, 0.f), rs = ls;
-                c[fr] = ls;
-                if (g != 0.f) split_gain_mask(buf[lo], buf[hi], g, c[fr], ls, rs);
-                buf[lo] = make_float2(ls.x - rs.y, ls.y + rs.x);
-                buf[hi] = make_float2(ls.x + rs.y, rs.x - ls.y);
+                float2 ylo = make_float2(0.f, 0.f), yhi = ylo;
+                c[fr] = ylo;
+                if (g != 0.f) mask_bin(buf[lo], buf[hi], g, ylo, yhi, c[fr]);
+                buf[lo] = ylo;
+                buf[hi] = yhi;
             }
             float2* cb = S + 4 * RS;
             cb[lo] = make_float2(c[0].x - c[1].y, c[0].y + c[1].x);

@@ -17,7 +17,7 @@ constexpr int LARGE_MAX_N = 65536;
 struct BandDev {
     int n_fft;
     int hop;
-    const float* ana;          // [n_fft]       analysis window
+    const float* ana;          // [n_fft + 1]   analysis window, followed by one zero
     const float* syn;          // [n_fft]       synthesis window / n_fft (the inverse FFT is unnormalised)
     const float* gain;         // [n_fft/2+1]   band-limit gain
     const float2* tw_fft;      // per-pass twiddles (fft_device.cuh layout) of the n_fft-point transform
