@@ -125,6 +125,17 @@ int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, con
 int upmix_process_host(const UpmixPlan* plan, const float* L, const float* R, int64_t n_samples, float* out_c,
                        float* out_l, float* out_r);
 
+/* main.py's tail on the device.  upmix_peak3: peaks3[0..2] (device) = max|C|, max|Ls|, max|Rs| over n
+ * samples (main.py:85-88); workspace of upmix_peak_workspace_bytes() device bytes.  upmix_export_mix:
+ * scales C/Ls/Rs by `scale` (main.py:90-97) and writes interleaved stereo float32 [n][2]:
+ * mode 0 "AB" out_a = (Ls+C+Rs, L+R) (main.py:110-119); mode 1 "split" out_a = (Ls,0), out_b = (C,C),
+ * out_c = (0,Rs) (main.py:125-141); mode 2 "stereo_sum" out_a = (Ls+C/2, Rs+C/2) (main.py:143-153). */
+int64_t upmix_peak_workspace_bytes(void);
+int upmix_peak3(const float* c, const float* l, const float* r, int64_t n, float* peaks3, void* workspace,
+                int64_t workspace_bytes, void* stream);
+int upmix_export_mix(int mode, float scale, const float* c, const float* l, const float* r, const float* in_l,
+                     const float* in_r, int64_t n, float* out_a, float* out_b, float* out_c, void* stream);
+
 /* Measurement helpers (bench.py): number of kernels this library launched since the last reset, and
  * the FP32 FMA throughput of the device (the roofline denominator of this FP32-bound path). */
 int64_t upmix_debug_launch_count(int reset);

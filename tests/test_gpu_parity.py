@@ -317,3 +317,29 @@ def test_main_driver_writes_reference_named_files(ce, tmp_path):
     with pytest.raises(FileNotFoundError):
         drv.run("missing.wav", "AB", str(in_dir), str(out_dir))
     assert quiet(drv.run, "noise.wav", "bogus", str(in_dir), str(out_dir), [0, 500, 4000], max_block_size=8192) == []
+
+
+def test_device_peak_and_export_mixes(ce):
+    """upmix_peak3 / upmix_export_mix against main.py's numpy arithmetic (main.py:85-97, 110-157)."""
+    import torch
+    from upmix_b200 import _native
+    rng = np.random.default_rng(3)
+    n = 100003
+    c, l, r, il, ir = (rng.standard_normal(n).astype(np.float32) * 0.2 for _ in range(5))
+    c[777] = -1.7
+    dc, dl, dr, dil, dir_ = (torch.from_numpy(x).cuda() for x in (c, l, r, il, ir))
+    pk = _native.peak3(dc, dl, dr).cpu().numpy()
+    assert np.array_equal(pk, np.array([np.abs(c).max(), np.abs(l).max(), np.abs(r).max()], dtype=np.float32))
+    scale = np.float32(0.37)
+    sc, sl, sr_ = c * scale, l * scale, r * scale
+    ab = _native.export_mix("AB", float(scale), dc, dl, dr, dil, dir_)[0].cpu().numpy()
+    assert np.array_equal(ab[:, 0], (sl + sc) + sr_) and np.array_equal(ab[:, 1], il + ir)
+    sp = [o.cpu().numpy() for o in _native.export_mix("split", float(scale), dc, dl, dr)]
+    assert np.array_equal(sp[0][:, 0], sl) and not sp[0][:, 1].any()
+    assert np.array_equal(sp[1][:, 0], sc) and np.array_equal(sp[1][:, 1], sc)
+    assert np.array_equal(sp[2][:, 1], sr_) and not sp[2][:, 0].any()
+    ss = _native.export_mix("stereo_sum", float(scale), dc, dl, dr)[0].cpu().numpy()
+    # FMA contraction on the device: within one rounding of the two-step numpy result
+    assert np.max(np.abs(ss[:, 0] - (sl + np.float32(0.5) * sc))) <= 1.2e-7 and np.max(np.abs(ss[:, 1] - (sr_ + np.float32(0.5) * sc))) <= 1.2e-7
+    with pytest.raises(ValueError):
+        _native.export_mix("nope", 1.0, dc, dl, dr)

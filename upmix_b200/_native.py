@@ -68,6 +68,9 @@ def load_library():
     _sig(lib.upmix_stream_block, i32, [vp, vp, i64, vp, vp, i32, i32, i64, vp, vp, vp, i64, vp, i64, vp])
     _sig(lib.upmix_process_host, i32, [vp, vp, vp, i64, vp, vp, vp])
     _sig(lib.upmix_frame_step, i32, [vp, vp, i64, vp, vp, i32, i64, vp, vp, vp, i64, vp, i64, vp])
+    _sig(lib.upmix_peak_workspace_bytes, i64, [])
+    _sig(lib.upmix_peak3, i32, [vp, vp, vp, i64, vp, vp, i64, vp])
+    _sig(lib.upmix_export_mix, i32, [i32, ctypes.c_float, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp])
     _sig(lib.upmix_debug_launch_count, i64, [i32])
     _sig(lib.upmix_measure_fp32_tflops, i32, [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)])
     _lib = lib
@@ -78,7 +81,42 @@ EXPORTS = ("upmix_last_error", "upmix_version", "upmix_plan_create", "upmix_plan
            "upmix_plan_n_bands", "upmix_workspace_bytes", "upmix_segment_halo", "upmix_process",
            "upmix_process_segment", "upmix_stream_state_bytes", "upmix_stream_workspace_bytes",
            "upmix_stream_delay", "upmix_stream_reset", "upmix_stream_block", "upmix_process_host",
-           "upmix_frame_step", "upmix_debug_launch_count", "upmix_measure_fp32_tflops")
+           "upmix_frame_step", "upmix_debug_launch_count", "upmix_measure_fp32_tflops",
+           "upmix_peak_workspace_bytes", "upmix_peak3", "upmix_export_mix")
+
+EXPORT_MODES = {"AB": 0, "split": 1, "stereo_sum": 2}
+
+
+def peak3(c, l, r):
+    """max|C|, max|Ls|, max|Rs| of three float32 CUDA tensors, as a 3-element CUDA tensor."""
+    torch = _torch()
+    lib = load_library()
+    n = c.numel()
+    out = torch.empty(3, dtype=torch.float32, device=c.device)
+    wsb = int(lib.upmix_peak_workspace_bytes())
+    ws = torch.empty(wsb, dtype=torch.uint8, device=c.device)
+    with torch.cuda.device(c.device):
+        _check(lib.upmix_peak3(c.data_ptr(), l.data_ptr(), r.data_ptr(), n, out.data_ptr(), ws.data_ptr(), wsb,
+                               torch.cuda.current_stream(c.device).cuda_stream))
+    return out
+
+
+def export_mix(mode: str, scale: float, c, l, r, in_l=None, in_r=None):
+    """Scaled export mix of main.py as interleaved stereo float32 CUDA tensors [n, 2] (one tensor,
+    three for "split")."""
+    torch = _torch()
+    lib = load_library()
+    if mode not in EXPORT_MODES:
+        raise ValueError(f"unknown export mode {mode!r}")
+    n = c.numel()
+    outs = [torch.empty((n, 2), dtype=torch.float32, device=c.device) for _ in range(3 if mode == "split" else 1)]
+    ptr = [o.data_ptr() for o in outs] + [None, None]
+    with torch.cuda.device(c.device):
+        _check(lib.upmix_export_mix(EXPORT_MODES[mode], float(scale), c.data_ptr(), l.data_ptr(), r.data_ptr(),
+                                    in_l.data_ptr() if in_l is not None else None,
+                                    in_r.data_ptr() if in_r is not None else None, n, ptr[0], ptr[1], ptr[2],
+                                    torch.cuda.current_stream(c.device).cuda_stream))
+    return outs
 
 
 def launch_count(reset: bool = False) -> int:

@@ -460,6 +460,30 @@ int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, con
                        out_r, out_stride, workspace, workspace_bytes, rings, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// ---- main.py's normalise + export on the device -------------------------------------------------
+int64_t upmix_peak_workspace_bytes(void) { return (int64_t)(3 * 1184 + 3) * (int64_t)sizeof(float); }
+
+int upmix_peak3(const float* c, const float* l, const float* r, int64_t n, float* peaks3, void* workspace,
+                int64_t workspace_bytes, void* stream) {
+    if (!c || !l || !r || !peaks3 || !workspace) return fail(UPMIX_E_INVALID, "NULL pointer");
+    if (n < 0) return fail(UPMIX_E_INVALID, "negative length");
+    if (workspace_bytes < upmix_peak_workspace_bytes()) return fail(UPMIX_E_WORKSPACE, "peak workspace too small");
+    int blocks = (int)std::min<int64_t>(1184, std::max<int64_t>(1, (n + 255) / 256));
+    CU_CHECK(launch_peak3(c, l, r, n, reinterpret_cast<float*>(workspace), blocks, peaks3, reinterpret_cast<cudaStream_t>(stream)));
+    return UPMIX_OK;
+}
+
+int upmix_export_mix(int mode, float scale, const float* c, const float* l, const float* r, const float* in_l,
+                     const float* in_r, int64_t n, float* out_a, float* out_b, float* out_c, void* stream) {
+    if (mode < 0 || mode > 2) return fail(UPMIX_E_INVALID, "unknown export mode %d", mode);
+    if (!c || !l || !r || !out_a) return fail(UPMIX_E_INVALID, "NULL pointer");
+    if (mode == 0 && (!in_l || !in_r)) return fail(UPMIX_E_INVALID, "AB export needs the input channels");
+    if (mode == 1 && (!out_b || !out_c)) return fail(UPMIX_E_INVALID, "split export needs three outputs");
+    if (n <= 0) return n == 0 ? UPMIX_OK : fail(UPMIX_E_INVALID, "negative length");
+    CU_CHECK(launch_export_mix(c, l, r, in_l, in_r, n, scale, mode, out_a, out_b, out_c, reinterpret_cast<cudaStream_t>(stream)));
+    return UPMIX_OK;
+}
+
 int64_t upmix_debug_launch_count(int reset) { return (int64_t)launch_count(reset != 0); }
 
 int upmix_measure_fp32_tflops(int device, double* tflops, int* sm_count) {

@@ -570,6 +570,83 @@ __global__ void __launch_bounds__(256) band_sum_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// main.py's tail on the device (main.py:85-97, 110-157): peak of the three outputs, then one scale
+// factor and the export mix written as interleaved stereo.
+// ---------------------------------------------------------------------------------------------
+// partial[3*blockIdx.x + ch] = max |x_ch| over this block's grid-stride share (max is order-free,
+// so the two-stage reduction is deterministic)
+__global__ void __launch_bounds__(256) peak3_kernel(const float* __restrict__ c, const float* __restrict__ l,
+                                                    const float* __restrict__ r, long long n, float* __restrict__ partial) {
+    float m[3] = {0.f, 0.f, 0.f};
+    const float* src[3] = {c, l, r};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) m[ch] = fmaxf(m[ch], fabsf(__ldg(src[ch] + i)));
+    }
+    __shared__ float sm[3][8];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        float v = m[ch];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((threadIdx.x & 31) == 0) sm[ch][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float v = 0.f;
+        for (int w = 0; w < 8; w++) v = fmaxf(v, sm[threadIdx.x][w]);
+        partial[3 * blockIdx.x + threadIdx.x] = v;
+    }
+}
+
+__global__ void peak3_final_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ out3) {
+    const int ch = threadIdx.x;
+    if (ch < 3) {
+        float v = 0.f;
+        for (int b = 0; b < n_blocks; b++) v = fmaxf(v, partial[3 * b + ch]);
+        out3[ch] = v;
+    }
+}
+
+// mode 0 "AB": (Ls+C+Rs, L+R) ; 1 "split": (Ls,0) (C,C) (0,Rs) ; 2 "stereo_sum": (Ls + C/2, Rs + C/2).
+// Ls, C, Rs are scaled first, in float32, like main.py:95-97; out_* are interleaved stereo [n][2].
+__global__ void __launch_bounds__(256) export_mix_kernel(const float* __restrict__ c, const float* __restrict__ l,
+                                                         const float* __restrict__ r, const float* __restrict__ in_l,
+                                                         const float* __restrict__ in_r, long long n, float scale, int mode,
+                                                         float2* __restrict__ out_a, float2* __restrict__ out_b,
+                                                         float2* __restrict__ out_c) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float vc = __ldg(c + i) * scale, vl = __ldg(l + i) * scale, vr = __ldg(r + i) * scale;
+        if (mode == 0) {
+            out_a[i] = make_float2((vl + vc) + vr, __ldg(in_l + i) + __ldg(in_r + i));
+        } else if (mode == 1) {
+            out_a[i] = make_float2(vl, 0.f);
+            out_b[i] = make_float2(vc, vc);
+            out_c[i] = make_float2(0.f, vr);
+        } else {
+            out_a[i] = make_float2(vl + 0.5f * vc, vr + 0.5f * vc);
+        }
+    }
+}
+
+cudaError_t launch_peak3(const float* c, const float* l, const float* r, long long n, float* partial, int n_blocks,
+                         float* out3, cudaStream_t st) {
+    peak3_kernel<<<n_blocks, 256, 0, st>>>(c, l, r, n, partial);
+    peak3_final_kernel<<<1, 32, 0, st>>>(partial, n_blocks, out3);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_export_mix(const float* c, const float* l, const float* r, const float* in_l, const float* in_r,
+                              long long n, float scale, int mode, float* out_a, float* out_b, float* out_c, cudaStream_t st) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    export_mix_kernel<<<(unsigned)blocks, 256, 0, st>>>(c, l, r, in_l, in_r, n, scale, mode, reinterpret_cast<float2*>(out_a),
+                                                        reinterpret_cast<float2*>(out_b), reinterpret_cast<float2*>(out_c));
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP32 peak probe: 8 independent FMA chains per thread, enough warps to fill every SM.  Used by
 // bench.py for the roofline denominator (MEASURED_PEAKS.json has no FP32 figure).
 // ---------------------------------------------------------------------------------------------

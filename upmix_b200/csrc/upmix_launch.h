@@ -18,6 +18,10 @@ cudaError_t launch_band_sum(const float* ws, int n_bands, int n_tracks, long lon
                             float* out_c, float* out_l, float* out_r, long long out_stride, int mode,
                             cudaStream_t st);
 
+cudaError_t launch_peak3(const float* c, const float* l, const float* r, long long n, float* partial, int n_blocks,
+                         float* out3, cudaStream_t st);
+cudaError_t launch_export_mix(const float* c, const float* l, const float* r, const float* in_l, const float* in_r,
+                              long long n, float scale, int mode, float* out_a, float* out_b, float* out_c, cudaStream_t st);
 cudaError_t launch_fma_peak(float* out, int blocks, int iters, cudaStream_t st);
 unsigned long long launch_count(bool reset);
 

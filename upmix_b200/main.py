@@ -43,43 +43,46 @@ def run(in_filename="eyes.wav", export_mode="stereo_sum", in_dir="in", out_dir="
     band_extractors = ce.chain_bands(list(band_edges), overlap=overlap, window_func=window_func, sr=sr,
                                      xover_mode=xover_mode, max_block_size=max_block_size,
                                      threshold_factor=threshold_factor, xo_fraction=xo_fraction)
-    final_center, final_left, final_right = ce.extract_center_left_right_multi_band_in_memory(L, R, sr, band_extractors)
+    # Extraction, peak measurement and the export mix all stay on the device; only the three peaks and
+    # the finished stereo file(s) cross PCIe (main.py:78-97, 110-157 of the reference do this in numpy).
+    from . import _native
+    torch = _native._torch()
+    dL = torch.from_numpy(np.ascontiguousarray(L, dtype=np.float32)).cuda()
+    dR = torch.from_numpy(np.ascontiguousarray(R, dtype=np.float32)).cuda()
+    final_center, final_left, final_right = ce.extract_center_left_right_multi_band_in_memory(dL, dR, sr, band_extractors)
 
-    peaks = [float(np.max(np.abs(x))) if x.size else 0.0 for x in (final_left, final_center, final_right)]
-    overall_peak = max(*peaks, 1e-9)
+    if dL.numel():
+        peak_c, peak_l, peak_r = (float(v) for v in _native.peak3(final_center, final_left, final_right).cpu())
+    else:
+        peak_c = peak_l = peak_r = 0.0
+    overall_peak = max(peak_l, peak_c, peak_r, 1e-9)
     scale_factor = peak_in / overall_peak
     print(f"Original peak = {peak_in:.4f}, L/C/R peak = {overall_peak:.4f}")
     print(f"Applying scale_factor = {scale_factor:.4f}")
-    final_left = final_left * scale_factor
-    final_center = final_center * scale_factor
-    final_right = final_right * scale_factor
 
     band_info_str = "_".join(f"b{bex.block_size}({int(bex.f_low)}-{int(bex.f_high)})" for bex in band_extractors)
     base_in_name = os.path.splitext(in_filename)[0]
     written = []
 
+    def mix(mode):
+        if dL.numel() == 0:
+            return [np.zeros((0, 2), dtype=np.float32)] * (3 if mode == "split" else 1)
+        return [o.cpu().numpy() for o in _native.export_mix(mode, scale_factor, final_center, final_left, final_right, dL, dR)]
+
     if export_mode == "AB":
-        upmix_sum = final_left + final_center + final_right
-        orig_sum = L + R
-        N = min(len(upmix_sum), len(orig_sum))
         out_path = os.path.join(out_dir, f"{base_in_name}_AB_{band_info_str}_ov{overlap:.2f}.wav")
-        write_wav(out_path, np.column_stack([upmix_sum[:N], orig_sum[:N]]), sr)
+        write_wav(out_path, mix("AB")[0], sr)
         written.append(out_path)
         print(f"[AB] Wrote 2-ch => {out_path}\n  Left  = (Ls + C + Rs)\n  Right = (L + R)\n")
     elif export_mode == "split":
-        for tag, stereo, what in (("Ls", np.column_stack([final_left, np.zeros_like(final_left)]), "Left=Ls, Right=0"),
-                                  ("C", np.column_stack([final_center, final_center]), "Left=C, Right=C"),
-                                  ("Rs", np.column_stack([np.zeros_like(final_right), final_right]), "Left=0, Right=Rs")):
+        for tag, stereo, what in zip(("Ls", "C", "Rs"), mix("split"), ("Left=Ls, Right=0", "Left=C, Right=C", "Left=0, Right=Rs")):
             path = os.path.join(out_dir, f"{base_in_name}_{tag}_{band_info_str}.wav")
             write_wav(path, stereo, sr)
             written.append(path)
             print(f"[Split] Wrote => {path} ({what})")
     elif export_mode == "stereo_sum":
-        left_ch = final_left + 0.5 * final_center
-        right_ch = final_right + 0.5 * final_center
-        N = min(len(left_ch), len(right_ch))
         out_path = os.path.join(out_dir, f"{base_in_name}_Sum_{band_info_str}_ov{overlap:.2f}.wav")
-        write_wav(out_path, np.column_stack([left_ch[:N], right_ch[:N]]), sr)
+        write_wav(out_path, mix("stereo_sum")[0], sr)
         written.append(out_path)
         print(f"[StereoSum] Wrote 2-ch => {out_path}\n  Left  = (Ls + C/2)\n  Right = (Rs + C/2)\n")
     else:
