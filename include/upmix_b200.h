@@ -67,6 +67,9 @@ int upmix_version(void);
 int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int device, UpmixPlan** out);
 int upmix_plan_destroy(UpmixPlan* plan);
 int upmix_plan_n_bands(const UpmixPlan* plan);
+/* Bands with identical STFTs (size, hop, both windows) are merged into one pipeline: they share the
+ * forward transform and, by linearity, the inverse transform and the overlap-add. */
+int upmix_plan_n_pipelines(const UpmixPlan* plan);
 
 /* Bytes of device workspace upmix_process / upmix_process_segment need for seg_len output samples
  * per track and n_tracks tracks (negative on error).  Any 256-byte-aligned device buffer will do. */

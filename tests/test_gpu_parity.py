@@ -343,3 +343,25 @@ def test_device_peak_and_export_mixes(ce):
     assert np.max(np.abs(ss[:, 0] - (sl + np.float32(0.5) * sc))) <= 1.2e-7 and np.max(np.abs(ss[:, 1] - (sr_ + np.float32(0.5) * sc))) <= 1.2e-7
     with pytest.raises(ValueError):
         _native.export_mix("nope", 1.0, dc, dl, dr)
+
+
+def test_equal_stft_bands_are_merged_and_still_match(ce, golden_dir):
+    """Bands with the same size/hop/windows run as one pipeline (shared forward and inverse transforms)."""
+    g = _load(golden_dir, "cfg4_8band96k.npz")
+    ext = quiet(ce.chain_bands, list(g["edges"]), 0.75, ce.make_blackman_harris, float(g["sr"]), "raised_cosine",
+                max_block_size=8192)
+    plan = ce.plan_for(ext)
+    assert [e.block_size for e in ext].count(8192) == 4 and plan.n_pipelines == 5
+    ext1 = quiet(ce.chain_bands, [0, 30, 120, 480, 1920, 7680], 0.75, ce.make_blackman_harris, 48000, "raised_cosine")
+    assert ce.plan_for(ext1).n_pipelines == 5
+    # different windows are not merged
+    a = ce.MultiBandExtractorAccu(1024, 0.75, ce.make_hann, 100.0, 1000.0, 48000)
+    b = ce.MultiBandExtractorAccu(1024, 0.75, ce.make_blackman_harris, 1000.0, 5000.0, 48000)
+    assert ce.plan_for([a, b]).n_pipelines == 2
+    # merged result == sum of the single-band results (up to float32 rounding of the two summation orders)
+    L, R = uo.synth_stereo(60000, 8, stress=True)
+    whole = ce.extract_center_left_right_multi_band_in_memory(L, R, 96000.0, ext)
+    parts = [e.process_all_blocks(L, R) for e in ext]
+    for ch in range(3):
+        want = np.sum([p[ch].astype(np.float64) for p in parts], axis=0)
+        assert uo.snr_db(want, whole[ch]) > 120

@@ -56,6 +56,7 @@ def load_library():
     _sig(lib.upmix_plan_create, i32, [i32, ctypes.POINTER(_BandDesc), i32, i32, ctypes.POINTER(vp)])
     _sig(lib.upmix_plan_destroy, i32, [vp])
     _sig(lib.upmix_plan_n_bands, i32, [vp])
+    _sig(lib.upmix_plan_n_pipelines, i32, [vp])
     _sig(lib.upmix_workspace_bytes, i64, [vp, i64, i32])
     _sig(lib.upmix_segment_halo, i64, [vp])
     _sig(lib.upmix_process, i32, [vp, vp, vp, i64, i32, i64, vp, vp, vp, i64, vp, i64, vp])
@@ -78,7 +79,7 @@ def load_library():
 
 
 EXPORTS = ("upmix_last_error", "upmix_version", "upmix_plan_create", "upmix_plan_destroy",
-           "upmix_plan_n_bands", "upmix_workspace_bytes", "upmix_segment_halo", "upmix_process",
+           "upmix_plan_n_bands", "upmix_plan_n_pipelines", "upmix_workspace_bytes", "upmix_segment_halo", "upmix_process",
            "upmix_process_segment", "upmix_stream_state_bytes", "upmix_stream_workspace_bytes",
            "upmix_stream_delay", "upmix_stream_reset", "upmix_stream_block", "upmix_process_host",
            "upmix_frame_step", "upmix_debug_launch_count", "upmix_measure_fp32_tflops",
@@ -173,6 +174,7 @@ class Plan:
         self._lib = lib
         self._ws = None
         self.halo = int(lib.upmix_segment_halo(self._h))
+        self.n_pipelines = int(lib.upmix_plan_n_pipelines(self._h))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

@@ -259,4 +259,25 @@ __device__ __forceinline__ void mask_bin(float2 a, float2 b, float g, float2& y_
     y_hi = make_float2(g * b.x - c.x - c.y, g * b.y - c.x + c.y);
 }
 
+// Bands that share an STFT (same size, hop and windows) share the forward transform and -- the inverse
+// transform and the overlap-add being linear -- the inverse too: their masked spectra are summed per
+// bin.  `gain` points at bin k of the first gain table; tables are `stride` floats apart and sorted per
+// bin so that the non-zero gains come first (g0 = the first one, already loaded).
+__device__ __forceinline__ void mask_bin_merged(float2 a, float2 b, float g0, const float* __restrict__ gain, int n_gains,
+                                                int stride, float2& y_lo, float2& y_hi, float2& c) {
+    y_lo = y_hi = c = make_float2(0.f, 0.f);
+    float g = g0;
+    int q = 0;
+#pragma unroll 1
+    while (g != 0.f) {
+        float2 yl, yh, cc;
+        mask_bin(a, b, g, yl, yh, cc);
+        y_lo = cadd(y_lo, yl);
+        y_hi = cadd(y_hi, yh);
+        c = cadd(c, cc);
+        if (++q >= n_gains) break;
+        g = __ldg(gain + (long long)q * stride);
+    }
+}
+
 }  // namespace upmix

@@ -59,7 +59,8 @@ constexpr int K3_HOPS_PER_RUN = 16;
 struct UpmixPlan {
     int device = 0;
     int out_mode = 0;
-    std::vector<BandDev> bands;
+    std::vector<BandDev> bands;  // one entry per pipeline: bands with identical STFTs are merged
+    int n_bands_in = 0;          // bands the caller described
     void* tables = nullptr;     // one device allocation holding every table
     int max_large_n = 0;        // largest n_fft handled by the four-step path (0: none)
     int64_t halo = 0;           // input margin a time shard needs on each side
@@ -212,7 +213,6 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
     *out = nullptr;
     if (n_bands < 1 || !bands) return fail(UPMIX_E_INVALID, "need at least one band");
     if (out_mode != UPMIX_OUT_LSCRS && out_mode != UPMIX_OUT_FOLD) return fail(UPMIX_E_INVALID, "unknown out_mode %d", out_mode);
-    int64_t floats = 0;
     for (int i = 0; i < n_bands; i++) {
         const UpmixBandDesc& d = bands[i];
         if (!d.ana || !d.syn || !d.gain) return fail(UPMIX_E_INVALID, "band %d: NULL table", i);
@@ -222,7 +222,29 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
             return fail(UPMIX_E_UNSUPPORTED, "band %d: hop=%d must be even and divide n_fft=%d", i, d.hop, d.n_fft);
         if (d.n_fft > FUSED_MAX_N && d.hop * 4 != d.n_fft)
             return fail(UPMIX_E_UNSUPPORTED, "band %d: n_fft=%d > %d requires hop = n_fft/4 (75%% overlap), got %d", i, d.n_fft, FUSED_MAX_N, d.hop);
-        floats += round_up(d.n_fft + 1, 64) + round_up(d.n_fft, 64) + round_up(d.n_fft / 2 + 1, 64);
+    }
+    // Bands whose STFT is identical (size, hop, both windows) run as ONE pipeline: they share the forward
+    // transform, get their own mask per bin, and -- inverse transform and overlap-add being linear -- share
+    // the inverse as well.  groups[g] = indices of the bands of pipeline g, in list order.
+    std::vector<std::vector<int>> groups;
+    for (int i = 0; i < n_bands; i++) {
+        bool placed = false;
+        for (auto& grp : groups) {
+            const UpmixBandDesc& h = bands[grp[0]];
+            const UpmixBandDesc& d = bands[i];
+            if (h.n_fft == d.n_fft && h.hop == d.hop && memcmp(h.ana, d.ana, sizeof(float) * d.n_fft) == 0 &&
+                memcmp(h.syn, d.syn, sizeof(float) * d.n_fft) == 0) {
+                grp.push_back(i);
+                placed = true;
+                break;
+            }
+        }
+        if (!placed) groups.push_back(std::vector<int>(1, i));
+    }
+    int64_t floats = 0;
+    for (const auto& grp : groups) {
+        const UpmixBandDesc& d = bands[grp[0]];
+        floats += round_up(d.n_fft + 1, 64) + round_up(d.n_fft, 64) + (int64_t)grp.size() * round_up(d.n_fft / 2 + 1, 64);
         if (d.n_fft > FUSED_MAX_N) {
             floats += 2LL * d.n_fft + round_up(2LL * fft_tw_size(row_plan(d.n_fft / COL_R)), 64);
         } else {
@@ -238,6 +260,7 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
     if (!p) return fail(UPMIX_E_INVALID, "out of host memory");
     p->device = device;
     p->out_mode = out_mode;
+    p->n_bands_in = n_bands;
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) p->sm_count = sms;
     std::vector<float> host((size_t)floats, 0.f);
@@ -260,8 +283,8 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
                 }
         }
     };
-    for (int i = 0; i < n_bands; i++) {
-        const UpmixBandDesc& d = bands[i];
+    for (const auto& grp : groups) {
+        const UpmixBandDesc& d = bands[grp[0]];
         BandDev b;
         b.n_fft = d.n_fft;
         b.hop = d.hop;
@@ -273,9 +296,22 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
         for (int n = 0; n < d.n_fft; n++) host[off + n] = d.syn[n] * inv_n;
         b.syn = dbase + off;
         off += round_up(d.n_fft, 64);
-        memcpy(&host[off], d.gain, sizeof(float) * (d.n_fft / 2 + 1));
-        b.gain = dbase + off;
-        off += round_up(d.n_fft / 2 + 1, 64);
+        {   // gain tables of the merged bands; per bin the non-zero gains first (band order kept)
+            const int nb = d.n_fft / 2 + 1;
+            const int64_t gs = round_up(nb, 64);
+            const int ng = (int)grp.size();
+            for (int k = 0; k < nb; k++) {
+                int q = 0;
+                for (int m = 0; m < ng; m++) {
+                    const float g = bands[grp[m]].gain[k];
+                    if (g != 0.f) host[off + q++ * gs + k] = g;
+                }
+            }
+            b.gain = dbase + off;
+            b.n_gains = ng;
+            b.gain_stride = (int)gs;
+            off += ng * gs;
+        }
         if (d.n_fft <= FUSED_MAX_N) {
             int pf = 0, ph = 0;
             fused_plans(d.n_fft, &pf, &ph);
@@ -334,7 +370,9 @@ int upmix_plan_destroy(UpmixPlan* plan) {
     return UPMIX_OK;
 }
 
-int upmix_plan_n_bands(const UpmixPlan* plan) { return plan ? (int)plan->bands.size() : fail(UPMIX_E_INVALID, "plan is NULL"); }
+int upmix_plan_n_bands(const UpmixPlan* plan) { return plan ? plan->n_bands_in : fail(UPMIX_E_INVALID, "plan is NULL"); }
+
+int upmix_plan_n_pipelines(const UpmixPlan* plan) { return plan ? (int)plan->bands.size() : fail(UPMIX_E_INVALID, "plan is NULL"); }
 
 int64_t upmix_workspace_bytes(const UpmixPlan* plan, int64_t seg_len, int n_tracks) {
     if (!plan) return fail(UPMIX_E_INVALID, "plan is NULL");

@@ -197,9 +197,9 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
                         const int km = (N - k) & (N - 1);
                         const float2 a1 = Z[PAD<PF>(k)], b1 = Z[PAD<PF>(km)];
                         const float2 a2 = Z[PAD<PF>(k2)], b2 = Z[PAD<PF>(M + k)];
-                        float2 c1 = make_float2(0.f, 0.f), y1 = c1, y1m = c1, c2 = c1, y2 = c1, y2m = c1;
-                        if (g1[i] != 0.f) mask_bin(a1, b1, g1[i], y1, y1m, c1);
-                        if (g2[i] != 0.f) mask_bin(a2, b2, g2[i], y2, y2m, c2);
+                        float2 c1, y1, y1m, c2, y2, y2m;
+                        mask_bin_merged(a1, b1, g1[i], gain + k, b.n_gains, b.gain_stride, y1, y1m, c1);
+                        mask_bin_merged(a2, b2, g2[i], gain + k2, b.n_gains, b.gain_stride, y2, y2m, c2);
                         Z[PAD<PF>(k)] = y1;
                         Z[PAD<PF>(km)] = y1m;
                         Z[PAD<PF>(k2)] = y2;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
     const int n_items = pr == 0 ? N2 + 1 : N2;
     {
         constexpr int ITM = (N2 + 1 + T - 1) / T;
-        int lo_a[ITM], hi_a[ITM];
+        int lo_a[ITM], hi_a[ITM], bin_a[ITM];
         float g_a[ITM];
 #pragma unroll
         for (int i = 0; i < ITM; i++) {                 // index arithmetic and gain loads first
@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
             lo_a[i] = lo_row * RS + PAD<PL>(lo_idx);
             hi_a[i] = hi_row * RS + PAD<PL>(hi_idx);
             g_a[i] = __ldg(gain + bin);
+            bin_a[i] = bin;
         }
 #pragma unroll
         for (int i = 0; i < ITM; i++) {
@@ -408,9 +409,8 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 #pragma unroll
             for (int fr = 0; fr < 2; fr++) {
                 float2* buf = S + 2 * fr * RS;
-                float2 ylo = make_float2(0.f, 0.f), yhi = ylo;
-                c[fr] = ylo;
-                if (g != 0.f) mask_bin(buf[lo], buf[hi], g, ylo, yhi, c[fr]);
+                float2 ylo, yhi;
+                mask_bin_merged(buf[lo], buf[hi], g, gain + bin_a[i], b.n_gains, b.gain_stride, ylo, yhi, c[fr]);
                 buf[lo] = ylo;
                 buf[hi] = yhi;
             }

@@ -19,7 +19,10 @@ struct BandDev {
     int hop;
     const float* ana;          // [n_fft + 1]   analysis window, followed by one zero
     const float* syn;          // [n_fft]       synthesis window / n_fft (the inverse FFT is unnormalised)
-    const float* gain;         // [n_fft/2+1]   band-limit gain
+    const float* gain;         // [n_gains][gain_stride] band-limit gains of the bands merged into this
+                               // pipeline (same n_fft/hop/windows); per bin the non-zero gains come first
+    int n_gains;
+    int gain_stride;           // >= n_fft/2+1
     const float2* tw_fft;      // per-pass twiddles (fft_device.cuh layout) of the n_fft-point transform
                                // (fused path) or of the n_fft/16-point row transform (large path)
     const float2* tw_half;     // per-pass twiddles of the n_fft/2-point transform (fused path)
