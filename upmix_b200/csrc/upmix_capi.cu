@@ -66,6 +66,7 @@ struct UpmixPlan {
     int64_t halo = 0;           // input margin a time shard needs on each side
     int64_t delay = 0;          // max over bands of n_fft - hop (block streaming latency)
     int sm_count = 148;
+    bool fold_in_freq = false;  // FOLD output and every pipeline fused: the centre is folded per bin
 };
 
 namespace {
@@ -144,6 +145,7 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
         a.seg_begin = std::max<int64_t>(seg_begin, 0);
         a.seg_end = prod_end;
         a.state = band_state ? band_state[bi] : nullptr;
+        a.fold = p->fold_in_freq ? 1 : 0;
         if (seg_begin < 0 || prod_end < seg_end) {
             // part of the requested range lies outside the track: those samples are zero
             CU_CHECK(cudaMemsetAsync(base, 0, (size_t)3 * n_tracks * lay.ws_seg * sizeof(float), st));
@@ -188,7 +190,8 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
             }
         }
     }
-    CU_CHECK(launch_band_sum(ws, nb, n_tracks, seg_len, lay.ws_seg, out_c, out_l, out_r, out_stride, p->out_mode, st));
+    CU_CHECK(launch_band_sum(ws, nb, n_tracks, seg_len, lay.ws_seg, out_c, out_l, out_r, out_stride,
+                             p->fold_in_freq ? 2 : p->out_mode, st));
     return UPMIX_OK;
 }
 
@@ -352,6 +355,7 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
         p->delay = std::max<int64_t>(p->delay, d.n_fft - d.hop);
         p->bands.push_back(b);
     }
+    p->fold_in_freq = out_mode == UPMIX_OUT_FOLD && p->max_large_n == 0;
     e = cudaMemcpy(p->tables, host.data(), (size_t)floats * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         cudaFree(p->tables);

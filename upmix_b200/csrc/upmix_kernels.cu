@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
     const int tid = threadIdx.x;
     const int H = b.hop;
     const int K = N / H;
+    const bool fold = a.fold != 0;
     const long long h0 = a.hop_begin + (long long)blockIdx.x * a.hops_per_run;
     const long long h1 = min(h0 + (long long)a.hops_per_run, a.hop_end);
     if (h0 >= h1) return;
@@ -200,17 +201,27 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
                         float2 c1, y1, y1m, c2, y2, y2m;
                         mask_bin_merged(a1, b1, g1[i], gain + k, b.n_gains, b.gain_stride, y1, y1m, c1);
                         mask_bin_merged(a2, b2, g2[i], gain + k2, b.n_gains, b.gain_stride, y2, y2m, c2);
+                        if (fold) {
+                            // (Ls + C/2) + i (Rs + C/2) = (Ls + i Rs) + (1+i) C/2: the fold-down is linear, so
+                            // it is taken here and the centre needs no transform of its own
+                            y1 = make_float2(y1.x + 0.5f * (c1.x - c1.y), y1.y + 0.5f * (c1.x + c1.y));
+                            y1m = make_float2(y1m.x + 0.5f * (c1.x + c1.y), y1m.y + 0.5f * (c1.x - c1.y));
+                            y2 = make_float2(y2.x + 0.5f * (c2.x - c2.y), y2.y + 0.5f * (c2.x + c2.y));
+                            y2m = make_float2(y2m.x + 0.5f * (c2.x + c2.y), y2m.y + 0.5f * (c2.x - c2.y));
+                        }
                         Z[PAD<PF>(k)] = y1;
                         Z[PAD<PF>(km)] = y1m;
                         Z[PAD<PF>(k2)] = y2;
                         Z[PAD<PF>(M + k)] = y2m;
-                        // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);
-                        // IFFT_M(z)[m] = c[2m] + i c[2m+1]
-                        const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
-                        const float2 B = make_float2(c1.x - c2.x, c1.y + c2.y);
-                        const float2 D = cmul(B, make_float2(wp[i].x, -wp[i].y));
-                        Cz[PAD<PH>(k)] = make_float2(A.x - D.y, A.y + D.x);
-                        if (k > 0) Cz[PAD<PH>(M - k)] = make_float2(A.x + D.y, D.x - A.y);
+                        if (!fold) {
+                            // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);
+                            // IFFT_M(z)[m] = c[2m] + i c[2m+1]
+                            const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
+                            const float2 B = make_float2(c1.x - c2.x, c1.y + c2.y);
+                            const float2 D = cmul(B, make_float2(wp[i].x, -wp[i].y));
+                            Cz[PAD<PH>(k)] = make_float2(A.x - D.y, A.y + D.x);
+                            if (k > 0) Cz[PAD<PH>(M - k)] = make_float2(A.x + D.y, D.x - A.y);
+                        }
                     }
                 }
             }
@@ -236,7 +247,7 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
                                    acc.y += v.y * wn.y;
                                    *q = acc;
                                });
-        fft_smem<PH, +1, T, 1, true>(Cz, tid, twh, ld_c, st_c);
+        if (!fold) fft_smem<PH, +1, T, 1, true>(Cz, tid, twh, ld_c, st_c);
 
         // ---- request the next frame's input, then emit --------------------------------------------
         if (f + 1 < h1) prefetch(f + 1);
@@ -248,6 +259,7 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
         const bool whole = e_lo == 0 && e_hi == H && (H % 4 == 0);
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
+            if (ch == 0 && fold) continue;                                  // no centre channel when folded
             float* __restrict__ po = outp[ch] + (s0 - a.out_begin);
             float* rg = ring + ch * N + base;
             if (whole && (reinterpret_cast<uintptr_t>(po) & 15) == 0) {      // CTA-uniform: vector copy-out
@@ -524,7 +536,8 @@ __global__ void __launch_bounds__(128, 4) col_inv_ola_kernel(const BandDev b, co
 // ---------------------------------------------------------------------------------------------
 // ws layout: [band][channel C,Ls,Rs][track][ws_seg] (ws_seg >= seg_len, multiple of 4).  Bands are added in list order, in float32, as
 // center_extraction.py:503-511 does.  mode 0: C, Ls, Rs.  mode 1 (fold-down, bela/upmix.cpp:295-303,
-// 487-490): out_l = sum_b (Ls_b + 0.5 C_b), out_r = sum_b (Rs_b + 0.5 C_b); out_c untouched.
+// 487-490): out_l = sum_b (Ls_b + 0.5 C_b), out_r = sum_b (Rs_b + 0.5 C_b); out_c untouched.  mode 2: the
+// band kernels already folded the centre in (SegArgs::fold): out_l = sum_b slot_l, out_r = sum_b slot_r.
 template <int VEC>
 __global__ void __launch_bounds__(256) band_sum_kernel(const float* __restrict__ ws, int n_bands, int n_tracks,
                                                        long long seg_len, long long ws_seg,
@@ -544,16 +557,17 @@ __global__ void __launch_bounds__(256) band_sum_kernel(const float* __restrict__
             const float* p = ws + bnd * band_stride + track * ws_seg + i * VEC;
             float vc[VEC], vl[VEC], vr[VEC];
             if (VEC == 4) {
-                *reinterpret_cast<float4*>(vc) = __ldcs(reinterpret_cast<const float4*>(p));
+                if (mode != 2) *reinterpret_cast<float4*>(vc) = __ldcs(reinterpret_cast<const float4*>(p));
                 *reinterpret_cast<float4*>(vl) = __ldcs(reinterpret_cast<const float4*>(p + ch_stride));
                 *reinterpret_cast<float4*>(vr) = __ldcs(reinterpret_cast<const float4*>(p + 2 * ch_stride));
             } else {
-                vc[0] = p[0]; vl[0] = p[ch_stride]; vr[0] = p[2 * ch_stride];
+                vc[0] = mode != 2 ? p[0] : 0.f; vl[0] = p[ch_stride]; vr[0] = p[2 * ch_stride];
             }
 #pragma unroll
             for (int j = 0; j < VEC; j++) {
                 if (mode == 0) { c[j] += vc[j]; l[j] += vl[j]; r[j] += vr[j]; }
-                else { l[j] += vl[j] + 0.5f * vc[j]; r[j] += vr[j] + 0.5f * vc[j]; }
+                else if (mode == 1) { l[j] += vl[j] + 0.5f * vc[j]; r[j] += vr[j] + 0.5f * vc[j]; }
+                else { l[j] += vl[j]; r[j] += vr[j]; }               // already folded by the band kernels
             }
         }
         const long long o = track * out_stride + i * VEC;

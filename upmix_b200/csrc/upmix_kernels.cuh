@@ -47,6 +47,8 @@ struct SegArgs {
     long long seg_begin, seg_end;
     long long hop_begin, hop_end;   // global hop indices to produce
     int hops_per_run;               // hops handled by one CTA / thread run (plus warm-up frames)
+    int fold;                       // fused kernel: fold the centre in the frequency domain -- emit
+                                    // Ls + 0.5 C and Rs + 0.5 C in the Ls / Rs slots, no C transform
     float* state;                   // optional streaming state [track][3][n_fft]: ring carried between calls
 };
 
