@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -52,7 +53,11 @@ struct DeviceGuard {
     }
 };
 
-constexpr int K3_HOPS_PER_RUN = 16;
+int k3_hops_per_run() {
+    static const int v = [] { const char* e = getenv("UPMIX_K3_RUN"); return e ? std::max(4, atoi(e)) : 32; }();
+    return v;
+}
+#define K3_HOPS_PER_RUN k3_hops_per_run()
 
 }  // namespace
 
@@ -90,7 +95,9 @@ Layout make_layout(const UpmixPlan* p, int64_t seg_len, int n_tracks) {
         for (const BandDev& b : p->bands)
             if (b.n_fft > FUSED_MAX_N) hop_min = std::min<int64_t>(hop_min, b.hop);
         const int64_t seg_hops = (seg_len + hop_min - 1) / hop_min + 1;
-        int64_t wh = std::max<int64_t>(16, 512 / std::max(1, n_tracks));
+        int64_t wave_total = 2048;     // hops per wave over all tracks (tuning knob: UPMIX_WAVE_HOPS)
+        if (const char* ev = getenv("UPMIX_WAVE_HOPS")) wave_total = std::max(16, atoi(ev));
+        int64_t wh = std::max<int64_t>(16, wave_total / std::max(1, n_tracks));
         wh = round_up(std::min<int64_t>(wh, round_up(seg_hops, K3_HOPS_PER_RUN)), K3_HOPS_PER_RUN);
         l.wave_hops = (int)wh;
         l.wave_frames = (int)wh + 6;
