@@ -365,3 +365,83 @@ def test_equal_stft_bands_are_merged_and_still_match(ce, golden_dir):
     for ch in range(3):
         want = np.sum([p[ch].astype(np.float64) for p in parts], axis=0)
         assert uo.snr_db(want, whole[ch]) > 120
+
+
+def test_multi_track_batch_with_large_band_and_strides(ce):
+    """Batches of tracks through the four-step path (waves shared by tracks), non-contiguous track strides."""
+    import torch
+    sr = 48000
+    ext = quiet(ce.chain_bands, [0, 1000], 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=16384)
+    plan = ce.plan_for(ext)
+    n = 70000
+    tracks = 5
+    big = torch.zeros((tracks, 2, n + 64), dtype=torch.float32, device="cuda")
+    for t in range(tracks):
+        L, R = uo.synth_stereo(n, 300 + t)
+        big[t, 0, :n] = torch.from_numpy(L).cuda()
+        big[t, 1, :n] = torch.from_numpy(R).cuda()
+    Ls, Rs = big[:, 0, :n], big[:, 1, :n]            # row stride 2*(n+64): strided views
+    out = plan.process(Ls, Rs)
+    bands = uo.chain([0, 1000], 0.75, uo.blackman_harris, sr, max_block=16384)
+    for t in (0, tracks - 1):
+        ref = uo.upmix_multiband(bands, Ls[t].cpu().numpy().astype(np.float64), Rs[t].cpu().numpy().astype(np.float64))
+        assert_parity(ref, [o[t].cpu().numpy() for o in out], 0.5, what=f"track {t}")
+        single = plan.process(Ls[t].contiguous(), Rs[t].contiguous())
+        for o, s in zip(out, single):
+            assert torch.equal(o[t], s)
+
+
+def test_c_abi_argument_errors(ce):
+    """Error codes and messages instead of exceptions or crashes across the boundary."""
+    import ctypes
+    import torch
+    from upmix_b200 import _native
+    lib = _native.load_library()
+    e = ce.MultiBandExtractorAccu(1024, 0.75, ce.make_blackman_harris, 200.0, 2000.0, 48000)
+    plan = ce.plan_for([e])
+    n = 5000
+    x = torch.zeros(n, device="cuda")
+    out = torch.zeros((3, n), device="cuda")
+    ws = torch.zeros(plan.workspace_bytes(n, 1), dtype=torch.uint8, device="cuda")
+    args = [plan._h, x.data_ptr(), x.data_ptr(), n, 1, n, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), n]
+    assert lib.upmix_process(*args, ws.data_ptr(), 16, None) == -4 and b"workspace too small" in lib.upmix_last_error()
+    assert lib.upmix_process(plan._h, None, x.data_ptr(), n, 1, n, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), n,
+                             ws.data_ptr(), ws.numel(), None) == -1
+    assert lib.upmix_process(*args[:4], 0, *args[5:], ws.data_ptr(), ws.numel(), None) == -1          # n_tracks = 0
+    # a shard whose input does not cover its halo
+    assert lib.upmix_process_segment(plan._h, x.data_ptr(), x.data_ptr(), 1000, 2000, n, 1000, 3000, 1, n, out[0].data_ptr(),
+                                     out[1].data_ptr(), out[2].data_ptr(), n, ws.data_ptr(), ws.numel(), None) == -1
+    assert b"halo" in lib.upmix_last_error()
+    # hop that does not divide the size, size above the supported range
+    w = np.ones(1024, np.float32)
+    gn = np.ones(513, np.float32)
+    with pytest.raises(_native.UpmixNativeError):
+        _native.Plan([(1024, 300, w, w, gn)])
+    with pytest.raises(_native.UpmixNativeError):
+        _native.Plan([(131072, 32768, np.ones(131072, np.float32), np.ones(131072, np.float32), np.ones(65537, np.float32))])
+    # fine call still works afterwards
+    assert lib.upmix_process(*args, ws.data_ptr(), ws.numel(), None) == 0
+    torch.cuda.synchronize()
+
+
+def test_fold_down_with_large_band_and_stream_multitrack(ce):
+    import torch
+    sr = 48000
+    ext = quiet(ce.chain_bands, [0, 300, 3000], 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=16384)
+    L, R = uo.synth_stereo(50000, 77)
+    c, l, r = ce.extract_center_left_right_multi_band_in_memory(L, R, sr, ext)
+    fl, fr = ce.extract_stereo_fold_down(L, R, sr, ext)
+    assert np.max(np.abs(fl - (l + 0.5 * c))) < 1e-6 and np.max(np.abs(fr - (r + 0.5 * c))) < 1e-6
+    # block streaming, two tracks at once == offline result delayed by stream.delay
+    small = quiet(ce.chain_bands, [0, 1000, 6000], 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=2048)
+    plan = ce.plan_for(small)
+    st = plan.stream_open(2)
+    n = 2048 * 12
+    A = torch.from_numpy(np.stack([uo.synth_stereo(n, 1)[0], uo.synth_stereo(n, 2)[0]])).cuda()
+    B = torch.from_numpy(np.stack([uo.synth_stereo(n, 1)[1], uo.synth_stereo(n, 2)[1]])).cuda()
+    off = plan.process(A, B)
+    blocks = [st.block(A[:, i:i + 512].contiguous(), B[:, i:i + 512].contiguous()) for i in range(0, n, 512)]
+    d = st.delay
+    for ch in range(3):
+        got = torch.cat([b[ch] for b in blocks], dim=1)
+        assert torch.equal(got[:, d:], off[ch][:, :n - d]) and not got[:, :d].any()
