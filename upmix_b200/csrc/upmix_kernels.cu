@@ -24,11 +24,15 @@ namespace upmix {
 // ---------------------------------------------------------------------------------------------
 // Per-size configuration of the fused kernel: radix plans of the N-point and N/2-point transforms,
 // threads per CTA (= per frame in flight) and the CTAs per SM the register budget is sized for.
+#ifndef UPMIX_TMA_MIN_N
+#define UPMIX_TMA_MIN_N 2048      // frames of this size and larger are staged by TMA bulk copies
+#endif
 template <int N> struct FusedCfg;
 #define UPMIX_FUSED_CFG_X(N_, ...) UPMIX_FUSED_CFG(N_, __VA_ARGS__)
 #define UPMIX_FUSED_CFG(N_, FULL_, HALF_, T_, MINB_)                                                     \
     template <> struct FusedCfg<N_> {                                                                     \
         static constexpr int FULL = FULL_, HALF = HALF_, T = T_, MINB = MINB_;                            \
+        static constexpr bool TMA = N_ >= UPMIX_TMA_MIN_N;                            \
         static_assert(fft_size(FULL_) == N_ && fft_size(HALF_) == N_ / 2, "plan does not match the size"); \
         static constexpr int SMEM = (PADSZ<FULL_>() + PADSZ<HALF_>()) * (int)sizeof(float2) + 3 * N_ * (int)sizeof(float); \
     };
@@ -113,19 +117,66 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
     const float2* __restrict__ twh = b.tw_half;
     const float2* __restrict__ twp = b.tw_pack;
 
-    // Input prefetch: the raw samples and window values of the NEXT frame are requested before the
-    // current frame's emit loop and consumed by the next iteration's first FFT pass.  xin[it][r] is
-    // point n = tid + it*T + r*NB0 of the frame, exactly what pass 0 asks for.
+    // Frame staging, two variants (FusedCfg<N>::TMA, chosen by measurement):
+    //  * TMA (N >= 2048): the raw samples of a frame land in the (then idle) transform buffer Z as two
+    //    planar arrays SL[N], SR[N]: one elected thread issues two bulk copies (cp.async.bulk + mbarrier)
+    //    for the NEXT frame as soon as the inverse transform of Ls + i Rs has released Z, so the copy
+    //    overlaps the centre's inverse transform and the copy-out; pass 0 of the next frame reads SL/SR
+    //    from shared memory.  Frames not wholly inside [in_begin, in_end) (track / shard edges) or not
+    //    16-byte aligned are filled by all threads instead, zero outside the available samples.
+    //  * registers (small N, where a frame turns around too quickly for the extra barrier to pay): the
+    //    next frame's samples are requested before the current frame's copy-out and wait in registers;
+    //    xin[it][r] is point n = tid + it*T + r*NB0, exactly what pass 0 asks for.
+    // Either way the analysis-window values are requested at the same time and wait in registers.
+    constexpr bool TMA = FusedCfg<N>::TMA;
     constexpr int R0 = fft_radix(PF, 0);
     constexpr int NB0 = N / R0;
     constexpr int IT0 = (NB0 + T - 1) / T;
-    float2 xin[IT0][R0];
+    __shared__ __align__(8) uint64_t in_bar;
+    float* SL = reinterpret_cast<float*>(Z);
+    float* SR = SL + N;
     float xw[IT0][R0];
-    auto prefetch = [&](long long fr) {
+    float2 xin[TMA ? 1 : IT0][TMA ? 1 : R0];
+    const bool tma_ok = TMA && ((reinterpret_cast<uintptr_t>(inl) | reinterpret_cast<uintptr_t>(inr)) & 15) == 0 &&
+                        (a.in_begin & 3) == 0 && (H & 3) == 0;
+    uint32_t in_phase = 0;
+    bool in_by_tma = false;
+    if (TMA) {
+        if (tid == 0) mbar_init(&in_bar, 1);
+        __syncthreads();
+    }
+    auto stage = [&](long long fr) {          // every thread calls this; TMA: at a point where nobody uses Z
         const long long s0n = fr * H;
         const float* __restrict__ pl = inl + (s0n - a.in_begin);     // pl[n] is sample s0n + n
         const float* __restrict__ pr = inr + (s0n - a.in_begin);
-        if (s0n >= a.in_begin && s0n + N <= a.in_end) {              // whole frame available (CTA-uniform)
+        const bool whole = s0n >= a.in_begin && s0n + N <= a.in_end; // CTA-uniform
+        const int lo_n = (int)max(0LL, min((long long)N, a.in_begin - s0n));
+        const int hi_n = (int)max(0LL, min((long long)N, a.in_end - s0n));
+        if constexpr (TMA) {
+            in_by_tma = tma_ok && whole;
+            if (in_by_tma) {
+                if (tid == 0) {
+                    fence_proxy_async_smem();
+                    mbar_expect_tx(&in_bar, 2u * N * (uint32_t)sizeof(float));
+                    tma_load_1d(SL, pl, N * (uint32_t)sizeof(float), &in_bar);
+                    tma_load_1d(SR, pr, N * (uint32_t)sizeof(float), &in_bar);
+                }
+            } else {
+                for (int n = tid; n < N; n += T) {
+                    const bool ok = n >= lo_n && n < hi_n;
+                    SL[n] = ok ? __ldg(pl + n) : 0.f;
+                    SR[n] = ok ? __ldg(pr + n) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < IT0; it++) {
+                const int j = tid + it * T;
+                if (NB0 % T == 0 || j < NB0) {
+#pragma unroll
+                    for (int r = 0; r < R0; r++) xw[it][r] = __ldg(ana + j + r * NB0);
+                }
+            }
+        } else if (whole) {
 #pragma unroll
             for (int it = 0; it < IT0; it++) {
                 const int j = tid + it * T;
@@ -141,8 +192,6 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
             // Samples outside [in_begin, in_end) -- before the track, past its end, or another shard's --
             // read as zero: their loads are clamped to a valid sample and their window value is taken
             // from the zero stored after the table (ana[N] == 0), so the loads stay unconditional.
-            const int lo_n = (int)max(0LL, min((long long)N, a.in_begin - s0n));
-            const int hi_n = (int)max(0LL, min((long long)N, a.in_end - s0n));
             const bool any = hi_n > lo_n;
             const int lo_c = min(lo_n, N - 1);
 #pragma unroll 1
@@ -161,19 +210,25 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
             }
         }
     };
-    prefetch(f_begin);
+    stage(f_begin);
+    if (TMA && !in_by_tma) __syncthreads();
 
     for (long long f = f_begin; f < h1; ++f) {
         const long long s0 = f * H;
         const int base = (int)(f % K) * H;
 
         // ---- forward: Z = FFT_N( ana * (L + iR) ) -----------------------------------------------
-        auto ld_in = [&](int, int, int it, int r) -> float2 {
+        if (TMA && in_by_tma) {
+            mbar_wait(&in_bar, in_phase);
+            in_phase ^= 1;
+        }
+        auto ld_in = [&](int, int n, int it, int r) -> float2 {
             const float wn = xw[it][r];
-            return make_float2(xin[it][r].x * wn, xin[it][r].y * wn);
+            if constexpr (TMA) return make_float2(SL[n] * wn, SR[n] * wn);
+            else return make_float2(xin[it][r].x * wn, xin[it][r].y * wn);
         };
         auto st_z = make_store([&](int, int k, float2 v, NoAux) { Z[PAD<PF>(k)] = v; });
-        fft_smem<PF, -1, T, 1, false>(Z, tid, tw, ld_in, st_z);
+        fft_smem<PF, -1, T, 1, TMA>(Z, tid, tw, ld_in, st_z);      // TMA: in place, SL/SR live inside Z
 
         // ---- split / gain / mask; Y1 = Ls + i*Rs in place, C packed for the half-size inverse ---
         {
@@ -237,6 +292,7 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
                                     ring[2 * N + p] += v.y * wn;
                                 });
         fft_smem<PF, +1, T, 1, true>(Z, tid, tw, ld_z, st_lr);
+        if (TMA && f + 1 < h1) stage(f + 1);       // Z is idle from here to the next frame's first pass
         auto ld_c = [&](int, int n, int, int) -> float2 { return Cz[PAD<PH>(n)]; };
         auto st_c = make_store([&](int, int m) -> float2 { return __ldg(reinterpret_cast<const float2*>(syn) + m); },
                                [&](int, int m, float2 v, float2 wn) {
@@ -249,8 +305,7 @@ __global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_
                                });
         if (!fold) fft_smem<PH, +1, T, 1, true>(Cz, tid, twh, ld_c, st_c);
 
-        // ---- request the next frame's input, then emit --------------------------------------------
-        if (f + 1 < h1) prefetch(f + 1);
+        if (!TMA && f + 1 < h1) stage(f + 1);      // register variant: request the next frame before the copy-out
 
         // ---- emit the hop this frame finished, clear its ring slots --------------------------------
         const bool emit = f >= h0;
