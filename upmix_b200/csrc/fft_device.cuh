@@ -298,18 +298,20 @@ __device__ __forceinline__ void mask_bin(float2 a, float2 b, float g, float2& y_
 // bin so that the non-zero gains come first (g0 = the first one, already loaded).
 __device__ __forceinline__ void mask_bin_merged(float2 a, float2 b, float g0, const float* __restrict__ gain, int n_gains,
                                                 int stride, float2& y_lo, float2& y_hi, float2& c) {
-    y_lo = y_hi = c = make_float2(0.f, 0.f);
-    float g = g0;
-    int q = 0;
+    if (g0 == 0.f) {
+        y_lo = y_hi = c = make_float2(0.f, 0.f);
+        return;
+    }
+    mask_bin(a, b, g0, y_lo, y_hi, c);
 #pragma unroll 1
-    while (g != 0.f) {
+    for (int q = 1; q < n_gains; q++) {                  // single-band pipelines never enter
+        const float g = __ldg(gain + (long long)q * stride);
+        if (g == 0.f) break;
         float2 yl, yh, cc;
         mask_bin(a, b, g, yl, yh, cc);
         y_lo = cadd(y_lo, yl);
         y_hi = cadd(y_hi, yh);
         c = cadd(c, cc);
-        if (++q >= n_gains) break;
-        g = __ldg(gain + (long long)q * stride);
     }
 }
 
