@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -79,7 +79,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        """Start of the timed region: only samples taken after this count."""
+        self.t_mark = time.time()
 
     def stop(self):
         if not self.proc:
@@ -91,8 +95,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 6:
+        for ts, r in self.rows:
+            if len(r) < 6 or ts < getattr(self, "t_mark", 0.0):
                 continue
             try:
                 sm.append(float(r[0]))
@@ -211,11 +215,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                     # nvidia-smi needs a few hundred ms to come up: start before the warm-up
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    time.sleep(0.3)
+    sampler.mark()
     _native.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
