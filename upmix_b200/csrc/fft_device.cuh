@@ -20,8 +20,15 @@
 
 namespace upmix {
 
+// Complex add / subtract as ONE packed instruction (sm_100 add.f32x2, SASS FADD2): the butterflies are
+// add-heavy, and halving their instruction count frees issue slots (the FMA pipe itself is not the limit).
+#ifndef UPMIX_SCALAR_CADD
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
