@@ -72,6 +72,15 @@ struct UpmixPlan {
     int64_t delay = 0;          // max over bands of n_fft - hop (block streaming latency)
     int sm_count = 148;
     bool fold_in_freq = false;  // FOLD output and every pipeline fused: the centre is folded per bin
+    // Pipelines are independent until the band sum, so they are spread over a few plan-owned streams
+    // (forked from / joined to the caller's stream with events): co-resident CTAs of different pipelines
+    // fill each other's stalls and launch tails.  Pipelines of the four-step path share one scratch and
+    // therefore one stream.
+    static constexpr int N_AUX = 3;
+    cudaStream_t aux[N_AUX] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[N_AUX] = {nullptr, nullptr, nullptr};
+    bool multi_stream = false;
 };
 
 namespace {
@@ -134,9 +143,23 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
     char* scratch = reinterpret_cast<char*>(workspace) + lay.band_out_bytes;
     const int nb = (int)p->bands.size();
     const int64_t prod_end = std::min(seg_end, n_total);      // nothing is produced past the end of the track
+    const cudaStream_t caller = st;
+    const bool fork = p->multi_stream && nb > 1 && band_state == nullptr;
+    bool used[UpmixPlan::N_AUX] = {false, false, false};
+    int next_fused = 1;
+    if (fork) CU_CHECK(cudaEventRecord(p->ev_fork, caller));
 
     for (int bi = 0; bi < nb; bi++) {
         const BandDev& b = p->bands[bi];
+        if (fork) {
+            const int si = b.n_fft > FUSED_MAX_N ? 0 : next_fused;
+            if (b.n_fft <= FUSED_MAX_N) next_fused = next_fused == UpmixPlan::N_AUX - 1 ? 1 : next_fused + 1;
+            st = p->aux[si];
+            if (!used[si]) {
+                CU_CHECK(cudaStreamWaitEvent(st, p->ev_fork, 0));
+                used[si] = true;
+            }
+        }
         SegArgs a;
         a.in_l = L;
         a.in_r = R;
@@ -197,8 +220,15 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
             }
         }
     }
+    if (fork) {
+        for (int si = 0; si < UpmixPlan::N_AUX; si++)
+            if (used[si]) {
+                CU_CHECK(cudaEventRecord(p->ev_join[si], p->aux[si]));
+                CU_CHECK(cudaStreamWaitEvent(caller, p->ev_join[si], 0));
+            }
+    }
     CU_CHECK(launch_band_sum(ws, nb, n_tracks, seg_len, lay.ws_seg, out_c, out_l, out_r, out_stride,
-                             p->fold_in_freq ? 2 : p->out_mode, st));
+                             p->fold_in_freq ? 2 : p->out_mode, caller));
     return UPMIX_OK;
 }
 
@@ -363,6 +393,15 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
         p->bands.push_back(b);
     }
     p->fold_in_freq = out_mode == UPMIX_OUT_FOLD && p->max_large_n == 0;
+    {
+        const char* ev = getenv("UPMIX_STREAMS");
+        p->multi_stream = !(ev && atoi(ev) == 0);
+        bool ok = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int si = 0; si < UpmixPlan::N_AUX && ok; si++)
+            ok = cudaStreamCreateWithFlags(&p->aux[si], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p->ev_join[si], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) p->multi_stream = false;
+    }
     e = cudaMemcpy(p->tables, host.data(), (size_t)floats * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         cudaFree(p->tables);
@@ -376,6 +415,11 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
 int upmix_plan_destroy(UpmixPlan* plan) {
     if (!plan) return UPMIX_OK;
     DeviceGuard guard(plan->device);
+    for (int si = 0; si < UpmixPlan::N_AUX; si++) {
+        if (plan->aux[si]) cudaStreamDestroy(plan->aux[si]);
+        if (plan->ev_join[si]) cudaEventDestroy(plan->ev_join[si]);
+    }
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     cudaFree(plan->tables);
     delete plan;
     return UPMIX_OK;
