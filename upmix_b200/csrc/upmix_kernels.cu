@@ -24,6 +24,9 @@ namespace upmix {
 // ---------------------------------------------------------------------------------------------
 // Per-size configuration of the fused kernel: radix plans of the N-point and N/2-point transforms,
 // threads per CTA (= per frame in flight) and the CTAs per SM the register budget is sized for.
+#ifndef UPMIX_REG_CAP
+#define UPMIX_REG_CAP 255
+#endif
 #ifndef UPMIX_TMA_MIN_N
 #define UPMIX_TMA_MIN_N 2048      // frames of this size and larger are staged by TMA bulk copies
 #endif
@@ -32,7 +35,10 @@ template <int N> struct FusedCfg;
 #define UPMIX_FUSED_CFG(N_, FULL_, HALF_, T_, MINB_)                                                     \
     template <> struct FusedCfg<N_> {                                                                     \
         static constexpr int FULL = FULL_, HALF = HALF_, T = T_, MINB = MINB_;                            \
-        static constexpr bool TMA = N_ >= UPMIX_TMA_MIN_N;                            \
+        static constexpr bool TMA = N_ >= UPMIX_TMA_MIN_N;                                               \
+        /* registers per thread: the share of the file MINB co-resident CTAs leave, but never the whole \
+           file for one CTA -- UPMIX_REG_CAP keeps room for CTAs of other pipelines on the same SM */ \
+        static constexpr int MAXREG = (65536 / (T_ * MINB_) / 8 * 8) > UPMIX_REG_CAP ? UPMIX_REG_CAP : (65536 / (T_ * MINB_) / 8 * 8);                            \
         static_assert(fft_size(FULL_) == N_ && fft_size(HALF_) == N_ / 2, "plan does not match the size"); \
         static constexpr int SMEM = (PADSZ<FULL_>() + PADSZ<HALF_>()) * (int)sizeof(float2) + 3 * N_ * (int)sizeof(float); \
     };
@@ -73,7 +79,7 @@ UPMIX_FUSED_CFG_X(4096, UPMIX_CFG_4096)
 UPMIX_FUSED_CFG_X(8192, UPMIX_CFG_8192)
 
 template <int N>
-__global__ void __launch_bounds__(FusedCfg<N>::T, FusedCfg<N>::MINB) band_fused_kernel(const BandDev b, const SegArgs a) {
+__global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXREG) band_fused_kernel(const BandDev b, const SegArgs a) {
     constexpr int T = FusedCfg<N>::T;
     constexpr int M = N / 2;
     constexpr int PF = FusedCfg<N>::FULL, PH = FusedCfg<N>::HALF;
