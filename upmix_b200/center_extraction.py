@@ -324,10 +324,17 @@ def _check_supported(band_extractors: Sequence[MultiBandExtractorAccu]) -> None:
 _PLAN_CACHE: "list" = []      # [(key, extractors, plan)], most recent last
 
 
+def _fingerprint(bex) -> tuple:
+    """What a plan depends on: if any of this changes on an extractor, its plan is rebuilt."""
+    return (id(bex), int(bex.block_size), int(bex.hop_size), float(bex.f_low), float(bex.f_high), float(bex.sr),
+            str(bex.xover_mode), float(bex.xover_width_low_hz), float(bex.xover_width_high_hz),
+            id(bex.analysis_window), id(bex.synthesis_window))
+
+
 def plan_for(band_extractors: Sequence[MultiBandExtractorAccu], out_mode: int = _native.OUT_LSCRS) -> "_native.Plan":
-    """Native plan for a list of extractors (cached while the same extractor objects are used)."""
+    """Native plan for a list of extractors (cached while the same, unmodified extractor objects are used)."""
     torch = _native._torch()
-    key = (tuple(id(b) for b in band_extractors), out_mode, torch.cuda.current_device())
+    key = (tuple(_fingerprint(b) for b in band_extractors), out_mode, torch.cuda.current_device())
     for k, exts, plan in _PLAN_CACHE:
         if k == key and all(a is b for a, b in zip(exts, band_extractors)):
             return plan
