@@ -139,6 +139,13 @@ int upmix_peak3(const float* c, const float* l, const float* r, int64_t n, float
 int upmix_export_mix(int mode, float scale, const float* c, const float* l, const float* r, const float* in_l,
                      const float* in_r, int64_t n, float* out_a, float* out_b, float* out_c, void* stream);
 
+/* WAV edge (main.py:43-55, 119-153 read/write 16-bit PCM through soundfile): interleaved PCM16 stereo
+ * [n][2] -> planar float32 L, R (x/32768) and *peak = max|x| (main.py:53); interleaved float32 stereo ->
+ * PCM16 (clip, x32768, round to nearest even).  Workspace: upmix_peak_workspace_bytes(). */
+int upmix_pcm16_to_planar(const int16_t* interleaved, int64_t n, float* l, float* r, float* peak, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+int upmix_stereo_to_pcm16(const float* interleaved, int64_t n, int16_t* out, void* stream);
+
 /* Measurement helpers (bench.py): number of kernels this library launched since the last reset, and
  * the FP32 FMA throughput of the device (the roofline denominator of this FP32-bound path). */
 int64_t upmix_debug_launch_count(int reset);

@@ -445,3 +445,29 @@ def test_fold_down_with_large_band_and_stream_multitrack(ce):
     for ch in range(3):
         got = torch.cat([b[ch] for b in blocks], dim=1)
         assert torch.equal(got[:, d:], off[ch][:, :n - d]) and not got[:, :d].any()
+
+
+def test_pcm16_edge_kernels(ce):
+    """WAV edge on the device: int16 stereo -> planar float32 + peak, float32 stereo -> int16."""
+    import torch
+    from upmix_b200 import _native
+    rng = np.random.default_rng(9)
+    pcm = rng.integers(-32768, 32768, size=(70001, 2), dtype=np.int16)
+    pcm[5] = (-32768, 32767)
+    l, r, peak = _native.pcm16_to_planar(torch.from_numpy(pcm).cuda())
+    assert np.array_equal(l.cpu().numpy(), pcm[:, 0].astype(np.float32) / 32768.0)
+    assert np.array_equal(r.cpu().numpy(), pcm[:, 1].astype(np.float32) / 32768.0)
+    assert float(peak.cpu()[0]) == 1.0
+    x = (rng.standard_normal((50001, 2)) * 0.5).astype(np.float32)
+    x[0] = (1.5, -1.5)
+    x[1] = (0.5 / 32768.0, 1.5 / 32768.0)            # ties round to even: 0 and 2
+    got = _native.stereo_to_pcm16(torch.from_numpy(x).cuda()).cpu().numpy()
+    want = np.rint(np.clip(x.astype(np.float64), -1.0, 32767.0 / 32768.0) * 32768.0).astype(np.int16)
+    assert np.array_equal(got, want) and tuple(got[0]) == (32767, -32768) and tuple(got[1]) == (0, 2)
+    # round trip of representable samples is exact
+    back = _native.stereo_to_pcm16(torch.stack([l, r], dim=1).contiguous()).cpu().numpy()
+    assert np.array_equal(back, pcm)
+    # empty input through the drop-in call
+    e = ce.MultiBandExtractorAccu(1024, 0.75, ce.make_blackman_harris, 200.0, 2000.0, 48000)
+    z = torch.zeros(0, device="cuda")
+    assert all(o.numel() == 0 for o in ce.extract_center_left_right_multi_band_in_memory(z, z, 48000, [e]))

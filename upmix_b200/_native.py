@@ -72,6 +72,8 @@ def load_library():
     _sig(lib.upmix_peak_workspace_bytes, i64, [])
     _sig(lib.upmix_peak3, i32, [vp, vp, vp, i64, vp, vp, i64, vp])
     _sig(lib.upmix_export_mix, i32, [i32, ctypes.c_float, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp])
+    _sig(lib.upmix_pcm16_to_planar, i32, [vp, i64, vp, vp, vp, vp, i64, vp])
+    _sig(lib.upmix_stereo_to_pcm16, i32, [vp, i64, vp, vp])
     _sig(lib.upmix_debug_launch_count, i64, [i32])
     _sig(lib.upmix_measure_fp32_tflops, i32, [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)])
     _lib = lib
@@ -83,7 +85,8 @@ EXPORTS = ("upmix_last_error", "upmix_version", "upmix_plan_create", "upmix_plan
            "upmix_process_segment", "upmix_stream_state_bytes", "upmix_stream_workspace_bytes",
            "upmix_stream_delay", "upmix_stream_reset", "upmix_stream_block", "upmix_process_host",
            "upmix_frame_step", "upmix_debug_launch_count", "upmix_measure_fp32_tflops",
-           "upmix_peak_workspace_bytes", "upmix_peak3", "upmix_export_mix")
+           "upmix_peak_workspace_bytes", "upmix_peak3", "upmix_export_mix", "upmix_pcm16_to_planar",
+           "upmix_stereo_to_pcm16")
 
 EXPORT_MODES = {"AB": 0, "split": 1, "stereo_sum": 2}
 
@@ -99,6 +102,37 @@ def peak3(c, l, r):
     with torch.cuda.device(c.device):
         _check(lib.upmix_peak3(c.data_ptr(), l.data_ptr(), r.data_ptr(), n, out.data_ptr(), ws.data_ptr(), wsb,
                                torch.cuda.current_stream(c.device).cuda_stream))
+    return out
+
+
+def pcm16_to_planar(pcm):
+    """pcm: int16 CUDA tensor [n, 2] (interleaved stereo).  Returns (L, R, peak): planar float32 CUDA
+    tensors (x / 32768) and a 1-element tensor with max|x| over both channels."""
+    torch = _torch()
+    lib = load_library()
+    if pcm.dtype != torch.int16 or pcm.dim() != 2 or pcm.shape[1] != 2 or not pcm.is_contiguous():
+        raise TypeError("pcm must be a contiguous int16 CUDA tensor [n, 2]")
+    n = pcm.shape[0]
+    out = torch.empty((2, n), dtype=torch.float32, device=pcm.device)
+    peak = torch.zeros(1, dtype=torch.float32, device=pcm.device)
+    wsb = int(lib.upmix_peak_workspace_bytes())
+    ws = torch.empty(wsb, dtype=torch.uint8, device=pcm.device)
+    with torch.cuda.device(pcm.device):
+        _check(lib.upmix_pcm16_to_planar(pcm.data_ptr(), n, out[0].data_ptr(), out[1].data_ptr(), peak.data_ptr(),
+                                         ws.data_ptr(), wsb, torch.cuda.current_stream(pcm.device).cuda_stream))
+    return out[0], out[1], peak
+
+
+def stereo_to_pcm16(stereo):
+    """stereo: float32 CUDA tensor [n, 2].  Returns the int16 CUDA tensor [n, 2] a 16-bit WAV stores."""
+    torch = _torch()
+    lib = load_library()
+    if stereo.dtype != torch.float32 or stereo.dim() != 2 or stereo.shape[1] != 2 or not stereo.is_contiguous():
+        raise TypeError("stereo must be a contiguous float32 CUDA tensor [n, 2]")
+    out = torch.empty(stereo.shape, dtype=torch.int16, device=stereo.device)
+    with torch.cuda.device(stereo.device):
+        _check(lib.upmix_stereo_to_pcm16(stereo.data_ptr(), stereo.shape[0], out.data_ptr(),
+                                         torch.cuda.current_stream(stereo.device).cuda_stream))
     return out
 
 
@@ -225,6 +259,8 @@ class Plan:
         elif out.shape != (n_out, tracks, seg_len) or not out.is_contiguous() or out.dtype != torch.float32:
             raise ValueError(f"out must be a contiguous float32 tensor of shape {(n_out, tracks, seg_len)}")
         oc, ol, orr = (out[0], out[1], out[2]) if n_out == 3 else (None, out[0], out[1])
+        if seg_len == 0:
+            return tuple(o[0] for o in out) if squeeze else tuple(out[i] for i in range(n_out))
         wsb = self.workspace_bytes(seg_len, tracks)
         ws = self._workspace(wsb)
         stream = torch.cuda.current_stream(L.device).cuda_stream

@@ -577,6 +577,24 @@ int upmix_export_mix(int mode, float scale, const float* c, const float* l, cons
     return UPMIX_OK;
 }
 
+int upmix_pcm16_to_planar(const int16_t* interleaved, int64_t n, float* l, float* r, float* peak, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+    if (!interleaved || !l || !r || !peak || !workspace) return fail(UPMIX_E_INVALID, "NULL pointer");
+    if (n < 0) return fail(UPMIX_E_INVALID, "negative length");
+    if (workspace_bytes < upmix_peak_workspace_bytes()) return fail(UPMIX_E_WORKSPACE, "workspace too small");
+    const int blocks = (int)std::min<int64_t>(1184, std::max<int64_t>(1, (n + 255) / 256));
+    CU_CHECK(launch_pcm16_to_planar(interleaved, n, l, r, reinterpret_cast<float*>(workspace), blocks, peak,
+                                    reinterpret_cast<cudaStream_t>(stream)));
+    return UPMIX_OK;
+}
+
+int upmix_stereo_to_pcm16(const float* interleaved, int64_t n, int16_t* out, void* stream) {
+    if (!interleaved || !out) return fail(UPMIX_E_INVALID, "NULL pointer");
+    if (n <= 0) return n == 0 ? UPMIX_OK : fail(UPMIX_E_INVALID, "negative length");
+    CU_CHECK(launch_stereo_to_pcm16(interleaved, n, out, reinterpret_cast<cudaStream_t>(stream)));
+    return UPMIX_OK;
+}
+
 int64_t upmix_debug_launch_count(int reset) { return (int64_t)launch_count(reset != 0); }
 
 int upmix_measure_fp32_tflops(int device, double* tflops, int* sm_count) {

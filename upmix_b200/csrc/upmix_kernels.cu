@@ -704,6 +704,63 @@ __global__ void __launch_bounds__(256) export_mix_kernel(const float* __restrict
     }
 }
 
+// WAV edge: interleaved 16-bit PCM stereo [n][2] -> planar float32 (x / 32768, soundfile's float view of
+// PCM_16), and interleaved float32 stereo -> 16-bit PCM (clip to [-1, 32767/32768], x 32768, round to
+// nearest even), so that only 4 bytes per stereo sample cross PCIe in each direction.
+__global__ void __launch_bounds__(256) pcm16_to_planar_kernel(const short2* __restrict__ in, long long n, float* __restrict__ l,
+                                                              float* __restrict__ r, float* __restrict__ peak_partial) {
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const short2 v = in[i];
+        const float a = (float)v.x * (1.f / 32768.f), b = (float)v.y * (1.f / 32768.f);
+        l[i] = a;
+        r[i] = b;
+        m = fmaxf(m, fmaxf(fabsf(a), fabsf(b)));
+    }
+    __shared__ float sm[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = 0.f;
+        for (int w = 0; w < 8; w++) v = fmaxf(v, sm[w]);
+        peak_partial[blockIdx.x] = v;
+    }
+}
+
+__global__ void max_final_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ out) {
+    if (threadIdx.x == 0) {
+        float v = 0.f;
+        for (int b = 0; b < n_blocks; b++) v = fmaxf(v, partial[b]);
+        out[0] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) stereo_to_pcm16_kernel(const float2* __restrict__ in, long long n, short2* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 v = in[i];
+        const float a = fminf(fmaxf(v.x, -1.f), 32767.f / 32768.f) * 32768.f;
+        const float b = fminf(fmaxf(v.y, -1.f), 32767.f / 32768.f) * 32768.f;
+        out[i] = make_short2((short)__float2int_rn(a), (short)__float2int_rn(b));
+    }
+}
+
+cudaError_t launch_pcm16_to_planar(const short* in, long long n, float* l, float* r, float* partial, int n_blocks, float* peak,
+                                   cudaStream_t st) {
+    pcm16_to_planar_kernel<<<n_blocks, 256, 0, st>>>(reinterpret_cast<const short2*>(in), n, l, r, partial);
+    max_final_kernel<<<1, 32, 0, st>>>(partial, n_blocks, peak);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stereo_to_pcm16(const float* in, long long n, short* out, cudaStream_t st) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    stereo_to_pcm16_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float2*>(in), n, reinterpret_cast<short2*>(out));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_peak3(const float* c, const float* l, const float* r, long long n, float* partial, int n_blocks,
                          float* out3, cudaStream_t st) {
     peak3_kernel<<<n_blocks, 256, 0, st>>>(c, l, r, n, partial);

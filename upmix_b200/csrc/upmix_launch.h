@@ -18,6 +18,9 @@ cudaError_t launch_band_sum(const float* ws, int n_bands, int n_tracks, long lon
                             float* out_c, float* out_l, float* out_r, long long out_stride, int mode,
                             cudaStream_t st);
 
+cudaError_t launch_pcm16_to_planar(const short* in, long long n, float* l, float* r, float* partial, int n_blocks, float* peak,
+                                   cudaStream_t st);
+cudaError_t launch_stereo_to_pcm16(const float* in, long long n, short* out, cudaStream_t st);
 cudaError_t launch_peak3(const float* c, const float* l, const float* r, long long n, float* partial, int n_blocks,
                          float* out3, cudaStream_t st);
 cudaError_t launch_export_mix(const float* c, const float* l, const float* r, const float* in_l, const float* in_r,

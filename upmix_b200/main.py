@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 from . import center_extraction as ce
-from .wavio import read_wav, write_wav
+from .wavio import read_wav, read_wav_pcm16, write_wav, write_wav_pcm16
 
 
 def run(in_filename="eyes.wav", export_mode="stereo_sum", in_dir="in", out_dir="out",
@@ -29,14 +29,28 @@ def run(in_filename="eyes.wav", export_mode="stereo_sum", in_dir="in", out_dir="
     in_path = os.path.join(in_dir, in_filename)
     if not os.path.isfile(in_path):
         raise FileNotFoundError(f"File not found: {in_path}")
-    wave, sr = read_wav(in_path)
-    print(f"Loaded '{in_path}', sr={sr}, shape={wave.shape}")
-    if wave.ndim == 1:
-        wave = np.column_stack([wave, wave])
-    L = wave[:, 0]
-    R = wave[:, 1]
-
-    peak_in = np.max(np.abs(wave)) if wave.size else 0.0
+    # 16-bit PCM stereo (what soundfile writes by default) goes to the device as int16 and is converted
+    # there (x/32768, like soundfile's float view); anything else takes the float route.
+    from . import _native
+    torch = _native._torch()
+    pcm = read_wav_pcm16(in_path)
+    if pcm is not None:
+        pcm_data, sr = pcm
+        print(f"Loaded '{in_path}', sr={sr}, shape={pcm_data.shape}")
+        if pcm_data.shape[0]:
+            dL, dR, dpeak = _native.pcm16_to_planar(torch.from_numpy(pcm_data).cuda())
+            peak_in = float(dpeak.cpu()[0])
+        else:
+            dL = dR = torch.zeros(0, dtype=torch.float32, device="cuda")
+            peak_in = 0.0
+    else:
+        wave, sr = read_wav(in_path)
+        print(f"Loaded '{in_path}', sr={sr}, shape={wave.shape}")
+        if wave.ndim == 1:
+            wave = np.column_stack([wave, wave])
+        peak_in = float(np.max(np.abs(wave))) if wave.size else 0.0
+        dL = torch.from_numpy(np.ascontiguousarray(wave[:, 0], dtype=np.float32)).cuda()
+        dR = torch.from_numpy(np.ascontiguousarray(wave[:, 1], dtype=np.float32)).cuda()
     if peak_in <= 0.0:
         peak_in = 1e-9
 
@@ -44,11 +58,7 @@ def run(in_filename="eyes.wav", export_mode="stereo_sum", in_dir="in", out_dir="
                                      xover_mode=xover_mode, max_block_size=max_block_size,
                                      threshold_factor=threshold_factor, xo_fraction=xo_fraction)
     # Extraction, peak measurement and the export mix all stay on the device; only the three peaks and
-    # the finished stereo file(s) cross PCIe (main.py:78-97, 110-157 of the reference do this in numpy).
-    from . import _native
-    torch = _native._torch()
-    dL = torch.from_numpy(np.ascontiguousarray(L, dtype=np.float32)).cuda()
-    dR = torch.from_numpy(np.ascontiguousarray(R, dtype=np.float32)).cuda()
+    # the finished 16-bit stereo file(s) cross PCIe (main.py:78-97, 110-157 of the reference do this in numpy).
     final_center, final_left, final_right = ce.extract_center_left_right_multi_band_in_memory(dL, dR, sr, band_extractors)
 
     if dL.numel():
@@ -64,25 +74,26 @@ def run(in_filename="eyes.wav", export_mode="stereo_sum", in_dir="in", out_dir="
     base_in_name = os.path.splitext(in_filename)[0]
     written = []
 
-    def mix(mode):
+    def mix(mode):       # int16 [n, 2] arrays, converted on the device like soundfile's PCM_16 writer
         if dL.numel() == 0:
-            return [np.zeros((0, 2), dtype=np.float32)] * (3 if mode == "split" else 1)
-        return [o.cpu().numpy() for o in _native.export_mix(mode, scale_factor, final_center, final_left, final_right, dL, dR)]
+            return [np.zeros((0, 2), dtype=np.int16)] * (3 if mode == "split" else 1)
+        outs = _native.export_mix(mode, scale_factor, final_center, final_left, final_right, dL, dR)
+        return [_native.stereo_to_pcm16(o).cpu().numpy() for o in outs]
 
     if export_mode == "AB":
         out_path = os.path.join(out_dir, f"{base_in_name}_AB_{band_info_str}_ov{overlap:.2f}.wav")
-        write_wav(out_path, mix("AB")[0], sr)
+        write_wav_pcm16(out_path, mix("AB")[0], sr)
         written.append(out_path)
         print(f"[AB] Wrote 2-ch => {out_path}\n  Left  = (Ls + C + Rs)\n  Right = (L + R)\n")
     elif export_mode == "split":
         for tag, stereo, what in zip(("Ls", "C", "Rs"), mix("split"), ("Left=Ls, Right=0", "Left=C, Right=C", "Left=0, Right=Rs")):
             path = os.path.join(out_dir, f"{base_in_name}_{tag}_{band_info_str}.wav")
-            write_wav(path, stereo, sr)
+            write_wav_pcm16(path, stereo, sr)
             written.append(path)
             print(f"[Split] Wrote => {path} ({what})")
     elif export_mode == "stereo_sum":
         out_path = os.path.join(out_dir, f"{base_in_name}_Sum_{band_info_str}_ov{overlap:.2f}.wav")
-        write_wav(out_path, mix("stereo_sum")[0], sr)
+        write_wav_pcm16(out_path, mix("stereo_sum")[0], sr)
         written.append(out_path)
         print(f"[StereoSum] Wrote 2-ch => {out_path}\n  Left  = (Ls + C/2)\n  Right = (Rs + C/2)\n")
     else:

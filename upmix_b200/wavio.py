@@ -26,6 +26,31 @@ def read_wav(path: str):
     return wave, int(sr)
 
 
+def read_wav_pcm16(path: str):
+    """(int16 array [frames, 2], sr) when the file is 16-bit PCM stereo and can be read without
+    conversion (scipy / stdlib path), else None: main.py then takes the float route."""
+    try:
+        from scipy.io import wavfile
+        sr, data = wavfile.read(path)
+    except Exception:
+        return None
+    if data.dtype != np.int16 or data.ndim != 2 or data.shape[1] != 2:
+        return None
+    return np.ascontiguousarray(data), int(sr)
+
+
+def write_wav_pcm16(path: str, pcm: np.ndarray, sr: int) -> None:
+    """Store int16 samples [frames, channels] as a 16-bit PCM WAV."""
+    try:
+        import soundfile as sf
+        sf.write(path, pcm, sr, subtype="PCM_16")
+        return
+    except ImportError:
+        pass
+    from scipy.io import wavfile
+    wavfile.write(path, int(sr), np.ascontiguousarray(pcm, dtype=np.int16))
+
+
 def write_wav(path: str, data: np.ndarray, sr: int) -> None:
     try:
         import soundfile as sf
