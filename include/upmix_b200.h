@@ -112,12 +112,14 @@ int upmix_stream_block(const UpmixPlan* plan, void* state, int64_t samples_done,
                        int n_new, int n_tracks, int64_t in_stride, float* out_c, float* out_l, float* out_r,
                        int64_t out_stride, void* workspace, int64_t workspace_bytes, void* stream);
 
-/* One frame of a single-band plan (n_fft <= 8192), the stateful API of the prototype
+/* One frame of a single-band plan, the stateful API of the prototype
  * (process_stereo_chunk, CE:353-409): blk_l / blk_r hold the n_fft samples of frame `frame_index`
  * (device), `ring` is the caller-owned overlap-add state [track][3][n_fft] floats (zero it to start;
  * its contents are the prototype's accumC/accumL/accumR, which is also what flush_final returns,
  * CE:411-424), out_* receive the hop samples the frame finishes.  frame_index must increase by one
- * per call.  Workspace: upmix_workspace_bytes(plan, hop, n_tracks). */
+ * per call.  Workspace: upmix_workspace_bytes(plan, hop, n_tracks).  Sizes above 8192 take one track per
+ * call and Ls/C/Rs output (their centre is transformed with a zero partner frame, so the result agrees
+ * with upmix_process to float32 rounding rather than bit for bit). */
 int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, const float* blk_l, const float* blk_r,
                      int n_tracks, int64_t in_stride, float* out_c, float* out_l, float* out_r, int64_t out_stride,
                      void* workspace, int64_t workspace_bytes, void* stream);

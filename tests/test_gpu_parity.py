@@ -471,3 +471,25 @@ def test_pcm16_edge_kernels(ce):
     e = ce.MultiBandExtractorAccu(1024, 0.75, ce.make_blackman_harris, 200.0, 2000.0, 48000)
     z = torch.zeros(0, device="cuda")
     assert all(o.numel() == 0 for o in ce.extract_center_left_right_multi_band_in_memory(z, z, 48000, [e]))
+
+
+@pytest.mark.parametrize("n_fft", [2048, 16384])
+def test_chunk_api_every_path_vs_oracle(ce, n_fft):
+    """process_stereo_chunk on the fused and on the four-step path: consecutive frames of a signal give the
+    offline result hop by hop, flush_final gives the tail (center_extraction.py:353-424)."""
+    sr = 48000
+    f_low = 32.0 * sr / n_fft
+    e = ce.MultiBandExtractorAccu(n_fft, 0.75, ce.make_blackman_harris, f_low, 4 * f_low, sr, "raised_cosine", f_low / 4, f_low)
+    b = uo.make_band(n_fft, 0.75, uo.blackman_harris, f_low, 4 * f_low, sr, "raised_cosine", f_low / 4, f_low)
+    H = n_fft // 4
+    n = 6 * H + n_fft + 123
+    L, R = uo.synth_stereo(n, 5)
+    ref = uo.process_band_frames(b, L.astype(np.float64), R.astype(np.float64))
+    frames = -(-n // H)                                     # every frame that starts inside the signal (CE:448-460)
+    Lp = np.concatenate([L, np.zeros(frames * H + n_fft - n, np.float32)])
+    Rp = np.concatenate([R, np.zeros(frames * H + n_fft - n, np.float32)])
+    got = [np.stack(e.process_stereo_chunk(Lp[f * H:f * H + n_fft], Rp[f * H:f * H + n_fft])) for f in range(frames)]
+    got = np.concatenate(got, axis=1)                       # [3, frames*H]
+    tail = np.stack(e.flush_final())                        # [3, n_fft]
+    assert tail.shape == (3, n_fft)
+    assert_parity(ref, list(got[:, :n]), 0.5, what=f"chunks N={n_fft}")

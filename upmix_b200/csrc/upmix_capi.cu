@@ -544,13 +544,41 @@ int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, con
     if (!ring) return fail(UPMIX_E_INVALID, "ring is NULL");
     if (plan->bands.size() != 1) return fail(UPMIX_E_INVALID, "upmix_frame_step needs a single-band plan");
     const BandDev& b = plan->bands[0];
-    if (b.n_fft > FUSED_MAX_N) return fail(UPMIX_E_UNSUPPORTED, "frame stepping needs n_fft <= %d", FUSED_MAX_N);
     if (frame_index < 0) return fail(UPMIX_E_INVALID, "negative frame index");
     DeviceGuard guard(plan->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (b.n_fft > FUSED_MAX_N) {
+        // four-step path: the frame is slot 0 of a two-frame wave, its partner slot is zero
+        const Layout lay = make_layout(plan, b.hop, n_tracks);
+        if (workspace_bytes < lay.total) return fail(UPMIX_E_WORKSPACE, "workspace too small: %lld given, %lld needed", (long long)workspace_bytes, (long long)lay.total);
+        if (plan->out_mode != UPMIX_OUT_LSCRS) return fail(UPMIX_E_UNSUPPORTED, "frame stepping on the four-step path needs Ls/C/Rs output");
+        char* scratch = reinterpret_cast<char*>(workspace) + lay.band_out_bytes;
+        WaveArgs w;
+        w.a = reinterpret_cast<float2*>(scratch);
+        w.b1 = reinterpret_cast<float2*>(scratch + lay.a_bytes);
+        w.b2 = reinterpret_cast<float2*>(scratch + lay.a_bytes + lay.b1_bytes);
+        w.frame0 = 0;
+        w.n_frames = 2;
+        SegArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in_l = blk_l;
+        a.in_r = blk_r;
+        a.in_stride = in_stride;
+        a.in_begin = 0;
+        a.in_end = b.n_fft;
+        CU_CHECK(cudaMemsetAsync(w.a, 0, (size_t)n_tracks * 2 * b.n_fft * sizeof(float2), st));
+        WaveArgs w1 = w;
+        w1.n_frames = 1;                       // column transform of the one real frame ...
+        if (n_tracks != 1) return fail(UPMIX_E_UNSUPPORTED, "frame stepping on the four-step path handles one track per call");
+        CU_CHECK(launch_col_fwd(b, a, w1, n_tracks, st));
+        CU_CHECK(launch_row_mask(b, w, n_tracks, st));          // ... paired with the zero frame
+        CU_CHECK(launch_col_inv_frame(b, w, reinterpret_cast<float*>(ring), out_c, out_l, out_r, out_stride, n_tracks, st));
+        return UPMIX_OK;
+    }
     float* rings[1] = {reinterpret_cast<float*>(ring)};
     const int64_t s0 = frame_index * b.hop;
     return run_segment(plan, blk_l, blk_r, s0, s0 + b.n_fft, INT64_MAX / 4, s0, s0 + b.hop, n_tracks, in_stride, out_c, out_l,
-                       out_r, out_stride, workspace, workspace_bytes, rings, reinterpret_cast<cudaStream_t>(stream));
+                       out_r, out_stride, workspace, workspace_bytes, rings, st);
 }
 
 // ---- main.py's normalise + export on the device -------------------------------------------------

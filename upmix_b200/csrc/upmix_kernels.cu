@@ -592,6 +592,55 @@ __global__ void __launch_bounds__(128, 4) col_inv_ola_kernel(const BandDev b, co
     }
 }
 
+// Single-frame variant of K3 for the stateful chunk API (process_stereo_chunk, center_extraction.py:
+// 353-409) on the four-step path: the frame sits in slot 0 of a two-frame wave whose partner is zero.
+// One thread per column: finish the inverse transform, window, add into the caller's overlap-add ring
+// [track][3][N] (frame-local order), emit the first hop and shift the ring by one hop.  A hop is 4 rows
+// of the thread's own column, so the in-place shift touches nobody else's samples.
+__global__ void __launch_bounds__(128, 4) col_inv_frame_kernel(const BandDev b, const WaveArgs w, float* __restrict__ ring,
+                                                               float* __restrict__ out_c, float* __restrict__ out_l,
+                                                               float* __restrict__ out_r, long long out_stride) {
+    const int N = b.n_fft;
+    const int N2 = N / COL_R;
+    const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n2 >= N2) return;
+    const int track = blockIdx.z;
+    const float2* __restrict__ B2 = w.b2 + ((long long)track * (w.n_frames / 2) * COL_R) * N2 + n2;
+    const float2* __restrict__ B1 = w.b1 + ((long long)track * w.n_frames * COL_R) * N2 + n2;
+    float* rg = ring + (long long)track * 3 * N + n2;
+    float* outp[3] = {out_c + (long long)track * out_stride, out_l + (long long)track * out_stride,
+                      out_r + (long long)track * out_stride};
+    float wn[COL_R];
+#pragma unroll
+    for (int n1 = 0; n1 < COL_R; n1++) wn[n1] = __ldg(b.syn + n1 * N2 + n2);
+    float2 vc[COL_R], v[COL_R];
+#pragma unroll
+    for (int k1 = 0; k1 < COL_R; k1++) { vc[k1] = B2[(long long)k1 * N2]; v[k1] = B1[(long long)k1 * N2]; }
+    Dft<COL_R, +1>::run(vc);
+    Dft<COL_R, +1>::run(v);
+#pragma unroll
+    for (int n1 = 0; n1 < COL_R; n1++) {
+        const float val[3] = {vc[n1].x * wn[n1], v[n1].x * wn[n1], v[n1].y * wn[n1]};
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const float acc = rg[(long long)ch * N + n1 * N2] + val[ch];
+            if (n1 < COL_R / 4) outp[ch][n1 * N2 + n2] = acc;
+            else rg[(long long)ch * N + (n1 - COL_R / 4) * N2] = acc;
+        }
+    }
+#pragma unroll
+    for (int n1 = COL_R - COL_R / 4; n1 < COL_R; n1++)
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) rg[(long long)ch * N + n1 * N2] = 0.f;
+}
+
+cudaError_t launch_col_inv_frame(const BandDev& b, const WaveArgs& w, float* ring, float* out_c, float* out_l, float* out_r,
+                                 long long out_stride, int n_tracks, cudaStream_t st) {
+    const int n2 = b.n_fft / COL_R;
+    col_inv_frame_kernel<<<dim3((n2 + 127) / 128, 1, n_tracks), 128, 0, st>>>(b, w, ring, out_c, out_l, out_r, out_stride);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // band summation + output mode
 // ---------------------------------------------------------------------------------------------

@@ -14,6 +14,8 @@ cudaError_t launch_col_fwd(const BandDev& b, const SegArgs& a, const WaveArgs& w
 cudaError_t launch_row_mask(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st);
 cudaError_t launch_col_inv_ola(const BandDev& b, const SegArgs& a, const WaveArgs& w, int n_runs, int n_tracks,
                                cudaStream_t st);
+cudaError_t launch_col_inv_frame(const BandDev& b, const WaveArgs& w, float* ring, float* out_c, float* out_l, float* out_r,
+                                 long long out_stride, int n_tracks, cudaStream_t st);
 cudaError_t launch_band_sum(const float* ws, int n_bands, int n_tracks, long long seg_len, long long ws_seg,
                             float* out_c, float* out_l, float* out_r, long long out_stride, int mode,
                             cudaStream_t st);
