@@ -24,6 +24,9 @@ namespace upmix {
 // ---------------------------------------------------------------------------------------------
 // Per-size configuration of the fused kernel: radix plans of the N-point and N/2-point transforms,
 // threads per CTA (= per frame in flight) and the CTAs per SM the register budget is sized for.
+#ifndef UPMIX_TW_IN_ROW
+#define UPMIX_TW_IN_ROW 1     // four-step twiddles applied by the row kernel (1) or by the column kernels (0)
+#endif
 #ifndef UPMIX_REG_CAP
 #define UPMIX_REG_CAP 255
 #endif
@@ -388,8 +391,14 @@ __global__ void __launch_bounds__(128) col_fwd_kernel(const BandDev b, const Seg
     }
     Dft<COL_R, -1>::run(v);
     float2* dst = w.a + (((long long)track * w.n_frames + fl) * COL_R) * N2 + n2;
+#if UPMIX_TW_IN_ROW
 #pragma unroll
     for (int k1 = 0; k1 < COL_R; k1++) dst[(long long)k1 * N2] = v[k1];     // twiddled by the row kernel
+#else
+    dst[0] = v[0];
+#pragma unroll
+    for (int k1 = 1; k1 < COL_R; k1++) dst[(long long)k1 * N2] = cmul(v[k1], __ldg(b.tw_col + k1 * N2 + n2));
+#endif
 }
 
 template <int N2> struct RowCfg;
@@ -441,7 +450,11 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
     for (int g = 0; g < 2; g++) {
         auto ld = [&](int row, int n, int, int) -> float2 {      // A * W_N^{k1 n}: the four-step twiddle
             const int k1 = row ? kb : ka;
+#if UPMIX_TW_IN_ROW
             return cmul(A[(fbase + (long long)g * COL_R + k1) * N2 + n], __ldg(twc + k1 * N2 + n));
+#else
+            return A[(fbase + (long long)g * COL_R + k1) * N2 + n];
+#endif
         };
         float2* buf = S + 2 * g * RS;
         auto st = make_store([&](int row, int k, float2 v, NoAux) { buf[row * RS + PAD<PL>(k)] = v; });
@@ -501,11 +514,15 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
         auto ld = [&](int row, int n, int, int) -> float2 { return buf[row * RS + PAD<PL>(n)]; };
         float2* dst = g < 2 ? w.b1 + (fbase + (long long)g * COL_R) * N2
                             : w.b2 + (((long long)track * (w.n_frames / 2) + fp) * COL_R) * N2;
+#if UPMIX_TW_IN_ROW
         auto st = make_store([&](int row, int n) -> float2 { return __ldg(twc + (row ? kb : ka) * N2 + n); },
                              [&](int row, int n, float2 v, float2 t) {     // * conj W_N^{k1 n}
                                  const int k1 = row ? kb : ka;
                                  dst[(long long)k1 * N2 + n] = cmul(v, make_float2(t.x, -t.y));
                              });
+#else
+        auto st = make_store([&](int row, int n, float2 v, NoAux) { dst[(long long)(row ? kb : ka) * N2 + n] = v; });
+#endif
         fft_smem<PL, +1, T, 2, true>(buf, tid, tw, ld, st);
     }
     (void)N;
@@ -568,6 +585,10 @@ __global__ void __launch_bounds__(128, 4) col_inv_ola_kernel(const BandDev b, co
             float2 v[COL_R];
 #pragma unroll
             for (int k1 = 0; k1 < COL_R; k1++) v[k1] = B2[(long long)k1 * N2];
+#if !UPMIX_TW_IN_ROW
+#pragma unroll
+            for (int k1 = 1; k1 < COL_R; k1++) { const float2 t = __ldg(b.tw_col + k1 * N2 + n2); v[k1] = cmul(v[k1], make_float2(t.x, -t.y)); }
+#endif
             Dft<COL_R, +1>::run(v);                          // v[n1] = (c_even[n], c_odd[n]), n = n1*N2 + n2
 #pragma unroll
             for (int n1 = 0; n1 < COL_R; n1++) {
@@ -580,6 +601,10 @@ __global__ void __launch_bounds__(128, 4) col_inv_ola_kernel(const BandDev b, co
             float2 v[COL_R];
 #pragma unroll
             for (int k1 = 0; k1 < COL_R; k1++) v[k1] = B1[((long long)half * COL_R + k1) * N2];
+#if !UPMIX_TW_IN_ROW
+#pragma unroll
+            for (int k1 = 1; k1 < COL_R; k1++) { const float2 t = __ldg(b.tw_col + k1 * N2 + n2); v[k1] = cmul(v[k1], make_float2(t.x, -t.y)); }
+#endif
             Dft<COL_R, +1>::run(v);
 #pragma unroll
             for (int n1 = 0; n1 < COL_R; n1++) {
@@ -616,6 +641,14 @@ __global__ void __launch_bounds__(128, 4) col_inv_frame_kernel(const BandDev b, 
     float2 vc[COL_R], v[COL_R];
 #pragma unroll
     for (int k1 = 0; k1 < COL_R; k1++) { vc[k1] = B2[(long long)k1 * N2]; v[k1] = B1[(long long)k1 * N2]; }
+#if !UPMIX_TW_IN_ROW
+#pragma unroll
+    for (int k1 = 1; k1 < COL_R; k1++) {
+        const float2 t = __ldg(b.tw_col + k1 * N2 + n2);
+        vc[k1] = cmul(vc[k1], make_float2(t.x, -t.y));
+        v[k1] = cmul(v[k1], make_float2(t.x, -t.y));
+    }
+#endif
     Dft<COL_R, +1>::run(vc);
     Dft<COL_R, +1>::run(v);
 #pragma unroll
