@@ -493,3 +493,23 @@ def test_chunk_api_every_path_vs_oracle(ce, n_fft):
     tail = np.stack(e.flush_final())                        # [3, n_fft]
     assert tail.shape == (3, n_fft)
     assert_parity(ref, list(got[:, :n]), 0.5, what=f"chunks N={n_fft}")
+
+
+@pytest.mark.parametrize("n_fft,top_bin", [(16384, 511), (16384, 512), (32768, 40), (65536, 511), (65536, 700)])
+def test_large_band_row_pruning_boundary(ce, n_fft, top_bin):
+    """Four-step path on both sides of the band-limited (pruned) row kernel's eligibility rule: every
+    non-zero gain below bin 512 -> pruned row transforms, otherwise the full ones.  Hard-zero pass band
+    [3, top_bin] so the last kept bin is exactly top_bin (rows 0 and 8 and their self-mirrored bins included)."""
+    sr = 48000
+    df = sr / n_fft
+    f_low, f_high = 3 * df, top_bin * df
+    e = ce.MultiBandExtractorAccu(n_fft, 0.75, ce.make_blackman_harris, f_low, f_high, sr, "hard_zero", 0.0, 0.0)
+    b = uo.make_band(n_fft, 0.75, uo.blackman_harris, f_low, f_high, sr, "hard_zero", 0.0, 0.0)
+    g = e.band_gain()
+    assert np.array_equal(g, b.gain) and int(np.nonzero(g)[0].max()) == top_bin
+    n = 2 * n_fft + 4321
+    L, R = uo.synth_stereo(n, 100 + top_bin, stress=True)
+    ref = uo.process_band_batched(b, L.astype(np.float64), R.astype(np.float64))
+    got = e.process_all_blocks(L, R)
+    peak = float(max(np.abs(L).max(), np.abs(R).max()))
+    assert_parity(ref, got, peak, what=f"N={n_fft} top_bin={top_bin}")

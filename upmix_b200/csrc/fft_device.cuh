@@ -258,18 +258,251 @@ __device__ __forceinline__ void fft_smem(float2* buf, int tid, const float2* __r
 }
 
 // ---------------------------------------------------------------------------------------------
+// Band-limited (pruned) row transforms of the four-step path.
+//
+// The dynamic-resolution rule puts the pass band of every band but the top one below bin ~430
+// (bin_low in [32, 64), bin_high = bin_low * f_high/f_low, plus the fade).  For the 16 x N2 four-step
+// split that means: of the N2 points of a row only the first K = 32 and -- their mirrors -- the last K
+// carry any gain.  The forward row transform then needs only those 2K outputs, and the inverse row
+// transform has only those 2K non-zero inputs.  With R0 = R1 = 16 (every row plan) the pruning is
+// static per pass:
+//   forward  pass 0: full;  pass 1: only outputs r with 16 r in [0,K) u [256-K,256) are consumed;
+//            pass 2: only butterflies j in [0,K) (output r = 0) and [NS-K, NS) (output r = R-1) run;
+//   inverse  pass 0: only butterflies j in [0,K) (single non-zero input r = 0) and [NB-K, NB) (single
+//            input r = 15) run;  pass 1: only inputs r whose block intersects [0,16K) u [N2-16K,N2) are
+//            non-zero;  pass 2: full.
+// Unneeded outputs are simply not stored (the compiler drops their arithmetic); known-zero inputs are
+// skipped by DftNZ, a DFT whose non-zero input set is a template mask.
+// ---------------------------------------------------------------------------------------------
+constexpr int ROW_K = 32;
+
+__host__ __device__ constexpr unsigned compact_bits(unsigned m, int r, int parity) {
+    unsigned o = 0;
+    for (int i = 0; i < r / 2; i++)
+        if ((m >> (2 * i + parity)) & 1u) o |= 1u << i;
+    return o;
+}
+
+// In-register radix-R DFT of inputs of which only those with their bit set in NZ are non-zero (the
+// others are never read).  Same recursion as Dft<R>, with the all-zero halves skipped.
+template <int R, int DIR, unsigned NZ>
+struct DftNZ {
+    static __device__ __forceinline__ void run(float2 (&v)[R]) {
+        constexpr unsigned NE = compact_bits(NZ, R, 0), NO = compact_bits(NZ, R, 1);
+        float2 e[R / 2], o[R / 2];
+#pragma unroll
+        for (int i = 0; i < R / 2; i++) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+        if constexpr (NE != 0) DftNZ<R / 2, DIR, NE>::run(e);
+        if constexpr (NO != 0) DftNZ<R / 2, DIR, NO>::run(o);
+#pragma unroll
+        for (int k = 0; k < R / 2; k++) {
+            if constexpr (NO == 0) {
+                const float2 x = NE != 0 ? e[k] : make_float2(0.f, 0.f);
+                v[k] = x;
+                v[k + R / 2] = x;
+            } else {
+                const float2 t = mul_w32<DIR>(o[k], k * (32 / R));
+                if constexpr (NE == 0) {
+                    v[k] = t;
+                    v[k + R / 2] = make_float2(-t.x, -t.y);
+                } else {
+                    v[k] = cadd(e[k], t);
+                    v[k + R / 2] = csub(e[k], t);
+                }
+            }
+        }
+    }
+};
+template <int DIR, unsigned NZ>
+struct DftNZ<1, DIR, NZ> {
+    static __device__ __forceinline__ void run(float2 (&)[1]) {}
+};
+
+// outputs r of forward pass 1 that some active butterfly of pass 2 reads (NS of pass 2 is 256)
+__host__ __device__ constexpr unsigned fwd_p1_out_mask(int K) {
+    unsigned m = 0;
+    for (int r = 0; r < 16; r++)
+        if (16 * r < K || 16 * (r + 1) > 256 - K) m |= 1u << r;
+    return m;
+}
+// inputs r of inverse pass 1 that can be non-zero: pass 0 fills [0, 16K) and [N2 - 16K, N2)
+__host__ __device__ constexpr unsigned inv_p1_in_mask(int n2, int K) {
+    const int nb1 = n2 / 16;
+    unsigned m = 0;
+    for (int r = 0; r < 16; r++)
+        if (nb1 * r < 16 * K || nb1 * (r + 1) > n2 - 16 * K) m |= 1u << r;
+    return m;
+}
+
+// Forward transform of two rows when only outputs [0,K) and [N2-K,N2) are needed (they alone are
+// written to buf; everything else in buf is left undefined).  PLAN = {16, 16, R2}.  ld as in fft_smem.
+template <int PLAN, int T, class Ld>
+__device__ __forceinline__ void fft_rows_fwd_pruned(float2* buf, int tid, const float2* __restrict__ tw, Ld ld) {
+    constexpr int N = fft_size(PLAN), RS = PADSZ<PLAN>(), K = ROW_K;
+    static_assert(fft_num_passes(PLAN) == 3 && fft_radix(PLAN, 0) == 16 && fft_radix(PLAN, 1) == 16, "row plans are {16,16,R}");
+    auto none = make_store([](int, int, float2, NoAux) {});
+    stockham_pass<PLAN, 0, -1, T, 2, false, Ld, decltype(none)>(buf, tid, tw, ld, none);
+    {   // pass 1: full butterflies, only the consumed outputs are stored
+        constexpr int R = 16, NS = 16, NB = N / R, TOTAL = 2 * NB, IT = (TOTAL + T - 1) / T;
+        constexpr unsigned OUT = fwd_p1_out_mask(K);
+        constexpr int LD_STR = NB + NB / 16, ST_STR = NS + NS / 16;
+        float2 v[IT][R], w[IT][R];
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int jj = tid + it * T;
+            if (TOTAL % T == 0 || jj < TOTAL) {
+                const int row = jj / NB, j = jj - row * NB, k = j & (NS - 1);
+                const float2* __restrict__ twp = tw + fft_tw_offset(PLAN, 1) + k;
+#pragma unroll
+                for (int r = 1; r < R; r++) w[it][r] = __ldg(twp + (r - 1) * NS);
+                const float2* __restrict__ src = buf + row * RS + PAD<PLAN>(j);
+#pragma unroll
+                for (int r = 0; r < R; r++) v[it][r] = src[r * LD_STR];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int jj = tid + it * T;
+            if (TOTAL % T == 0 || jj < TOTAL) {
+                const int row = jj / NB, j = jj - row * NB, k = j & (NS - 1);
+#pragma unroll
+                for (int r = 1; r < R; r++) v[it][r] = cmul(v[it][r], w[it][r]);
+                Dft<R, -1>::run(v[it]);
+                float2* __restrict__ dst = buf + row * RS + PAD<PLAN>((j - k) * R + k);
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if ((OUT >> r) & 1u) dst[r * ST_STR] = v[it][r];
+            }
+        }
+        __syncthreads();
+    }
+    {   // pass 2: 2K butterflies per row, one output each (r = 0 below, r = R-1 above)
+        constexpr int R = fft_radix(PLAN, 2), NS = 256, NB = N / R;
+        static_assert(NB == 256, "pass 2 of a row plan has 256 butterflies");
+        constexpr int LD_STR = NB + NB / 16;
+        const bool act = tid < 4 * K;                       // 2 rows x 2K butterflies
+        const int row = tid / (2 * K), a = tid - row * 2 * K;
+        const bool low = a < K;
+        const int j = low ? a : NS - 2 * K + a;
+        float2 v[R], w[R];
+        if (act) {
+            const float2* __restrict__ twp = tw + fft_tw_offset(PLAN, 2) + j;
+#pragma unroll
+            for (int r = 1; r < R; r++) w[r] = __ldg(twp + (r - 1) * NS);
+            const float2* __restrict__ src = buf + row * RS + PAD<PLAN>(j);
+#pragma unroll
+            for (int r = 0; r < R; r++) v[r] = src[r * LD_STR];
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int r = 1; r < R; r++) v[r] = cmul(v[r], w[r]);
+            if (low) {                                      // warp-uniform: K is a multiple of 32
+                float2 u[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) u[r] = v[r];
+                Dft<R, -1>::run(u);
+                buf[row * RS + PAD<PLAN>(j)] = u[0];
+            } else {
+                float2 u[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) u[r] = v[r];
+                Dft<R, -1>::run(u);
+                buf[row * RS + PAD<PLAN>(j + (R - 1) * NS)] = u[R - 1];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Inverse transform of two rows whose only non-zero inputs are [0,K) and [N2-K,N2) (the rest of buf is
+// never read).  st as in fft_smem (last pass output functor).
+template <int PLAN, int T, class St>
+__device__ __forceinline__ void fft_rows_inv_pruned(float2* buf, int tid, const float2* __restrict__ tw, St st) {
+    constexpr int N = fft_size(PLAN), RS = PADSZ<PLAN>(), K = ROW_K;
+    {   // pass 0: 2K butterflies per row, one non-zero input each
+        constexpr int R = 16, NB = N / R;
+        const bool act = tid < 4 * K;
+        const int row = tid / (2 * K), a = tid - row * 2 * K;
+        const bool low = a < K;
+        const int j = low ? a : NB - 2 * K + a;
+        float2 x = make_float2(0.f, 0.f);
+        if (act) x = buf[row * RS + PAD<PLAN>(low ? j : j + (R - 1) * NB)];
+        __syncthreads();
+        if (act) {
+            float2 v[R];
+            float2* __restrict__ dst = buf + row * RS + PAD<PLAN>(j * R);      // NS = 1: outputs j*16 + r, contiguous
+            if (low) {
+                v[0] = x;
+                DftNZ<R, +1, 1u>::run(v);
+            } else {
+                v[R - 1] = x;
+                DftNZ<R, +1, 1u << (R - 1)>::run(v);
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) dst[r] = v[r];
+        }
+        __syncthreads();
+    }
+    {   // pass 1: every butterfly, but only the inputs that pass 0 can have filled
+        constexpr int R = 16, NS = 16, NB = N / R, TOTAL = 2 * NB, IT = (TOTAL + T - 1) / T;
+        constexpr unsigned NZ = inv_p1_in_mask(N, K);
+        constexpr int LD_STR = NB + NB / 16, ST_STR = NS + NS / 16;
+        float2 v[IT][R], w[IT][R];
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int jj = tid + it * T;
+            if (TOTAL % T == 0 || jj < TOTAL) {
+                const int row = jj / NB, j = jj - row * NB, k = j & (NS - 1);
+                const float2* __restrict__ twp = tw + fft_tw_offset(PLAN, 1) + k;
+                const float2* __restrict__ src = buf + row * RS + PAD<PLAN>(j);
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if ((NZ >> r) & 1u) {
+                        if (r > 0) w[it][r] = __ldg(twp + (r - 1) * NS);
+                        v[it][r] = src[r * LD_STR];
+                    }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int jj = tid + it * T;
+            if (TOTAL % T == 0 || jj < TOTAL) {
+                const int row = jj / NB, j = jj - row * NB, k = j & (NS - 1);
+#pragma unroll
+                for (int r = 1; r < R; r++)
+                    if ((NZ >> r) & 1u) v[it][r] = cmul(v[it][r], make_float2(w[it][r].x, -w[it][r].y));
+                DftNZ<R, +1, NZ>::run(v[it]);
+                float2* __restrict__ dst = buf + row * RS + PAD<PLAN>((j - k) * R + k);
+#pragma unroll
+                for (int r = 0; r < R; r++) dst[r * ST_STR] = v[it][r];
+            }
+        }
+        __syncthreads();
+    }
+    auto nold = [](int, int, int, int) -> float2 { return make_float2(0.f, 0.f); };
+    stockham_pass<PLAN, 2, +1, T, 2, true, decltype(nold), St>(buf, tid, tw, nold, st);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Centre mask (reference: center_extraction.py:373-384; bela/upmix.cpp:363-385), float32.
 // coherence = |SL*conj(SR)| / (|SL||SR| + EPS) is evaluated as m / (m + EPS) with m = |SL||SR|
 // (identical in exact arithmetic), balance = (|SL|-|SR|) / (|SL|+|SR|+EPS).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sqrt_approx(float x) {       // MUFU-based, max rel. error 2^-22, sqrt(0) = 0
+// MUFU-based square root and reciprocal (max rel. error 2^-22), flush-to-zero variants: one SASS
+// instruction each (MUFU.SQRT / MUFU.RCP) -- the non-ftz forms carry a denormal rescue (FSETP + two
+// predicated FMULs) that the mask does not need: a denormal |P|^2 means a magnitude below 1e-19, where
+// the centre factor is ~m/EPS ~ 0 anyway, and the divisor is >= EPS^2 = 1e-24, a normal number.
+__device__ __forceinline__ float sqrt_approx(float x) {
     float y;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float div_approx(float a, float b) { // MUFU.RCP-based, 2 ulp, |b| in (2^-126, 2^126)
+__device__ __forceinline__ float rcp_approx(float x) {
     float y;
-    asm("div.approx.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
@@ -292,7 +525,7 @@ __device__ __forceinline__ void mask_bin(float2 a, float2 b, float g, float2& y_
     const float mr = hg * sqrt_approx(qx * qx + qy * qy);
     const float m = ml * mr;
     const float sden = ml + mr + EPS;
-    const float cf = div_approx(m * (sden - fabsf(ml - mr)), (m + EPS) * sden);
+    const float cf = (m * (sden - fabsf(ml - mr))) * rcp_approx((m + EPS) * sden);
     const float t = (0.5f * cf) * hg;
     c = make_float2(t * (px + qy), t * (py - qx));
     y_lo = make_float2(g * a.x - c.x + c.y, g * a.y - c.x - c.y);

@@ -340,12 +340,14 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
             const int nb = d.n_fft / 2 + 1;
             const int64_t gs = round_up(nb, 64);
             const int ng = (int)grp.size();
+            b.max_bin = -1;
             for (int k = 0; k < nb; k++) {
                 int q = 0;
                 for (int m = 0; m < ng; m++) {
                     const float g = bands[grp[m]].gain[k];
                     if (g != 0.f) host[off + q++ * gs + k] = g;
                 }
+                if (q) b.max_bin = k;
             }
             b.gain = dbase + off;
             b.n_gains = ng;

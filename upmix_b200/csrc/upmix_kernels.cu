@@ -13,6 +13,8 @@
 //                           and applies the output mode (Ls/C/Rs or L+0.5C / R+0.5C fold-down).
 //
 // Reference behaviour reproduced: center_extraction.py:353-472 (per-band chain), bela/upmix.cpp:238-306.
+#include <stdlib.h>
+
 #include "fft_device.cuh"
 #include "upmix_kernels.cuh"
 #include "upmix_launch.h"
@@ -81,7 +83,11 @@ UPMIX_FUSED_CFG_X(4096, UPMIX_CFG_4096)
 #endif
 UPMIX_FUSED_CFG_X(8192, UPMIX_CFG_8192)
 
-template <int N>
+// MODE selects the mask variant at compile time (the mask is ~45 % of a dense band's instructions):
+//   MODE_PLAIN  one band, Ls/C/Rs out;  MODE_FOLD  one band, centre folded per bin (SegArgs::fold);
+//   MODE_MERGED several bands share the pipeline (per-bin loop over their gains; fold read at run time).
+enum { MODE_PLAIN = 0, MODE_FOLD = 1, MODE_MERGED = 2 };
+template <int N, int MODE>
 __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXREG) band_fused_kernel(const BandDev b, const SegArgs a) {
     constexpr int T = FusedCfg<N>::T;
     constexpr int M = N / 2;
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
     const int tid = threadIdx.x;
     const int H = b.hop;
     const int K = N / H;
-    const bool fold = a.fold != 0;
+    const bool fold = MODE == MODE_MERGED ? a.fold != 0 : MODE == MODE_FOLD;
     const long long h0 = a.hop_begin + (long long)blockIdx.x * a.hops_per_run;
     const long long h1 = min(h0 + (long long)a.hops_per_run, a.hop_end);
     if (h0 >= h1) return;
@@ -240,6 +246,9 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
         fft_smem<PF, -1, T, 1, TMA>(Z, tid, tw, ld_in, st_z);      // TMA: in place, SL/SR live inside Z
 
         // ---- split / gain / mask; Y1 = Ls + i*Rs in place, C packed for the half-size inverse ---
+        // A thread takes bins k and M-k (and their mirrors N-k, M+k) per item, CH items per chunk.  A
+        // chunk whose gains are all zero only stores zeros (most of a low band's spectrum); otherwise the
+        // CH*2 masks are straight-line code, so their MUFU / dependency latencies overlap.
         {
             constexpr int ITM = (M / 2 + 1 + T - 1) / T;
             constexpr int CH = 3;                        // iterations whose table loads fly together
@@ -247,42 +256,71 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
             for (int it0 = 0; it0 < ITM; it0 += CH) {
                 float g1[CH], g2[CH];
                 float2 wp[CH];
+                bool any = false;
 #pragma unroll
                 for (int i = 0; i < CH; i++) {
                     const int k = min(tid + (it0 + i) * T, M / 2);
                     g1[i] = __ldg(gain + k);
                     g2[i] = __ldg(gain + M - k);
                     wp[i] = __ldg(twp + k);
+                    any = any || g1[i] != 0.f || g2[i] != 0.f;   // merged tables: non-zero gains come first
+                }
+                if (!any) {
+                    const float2 zero = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < CH; i++) {
+                        const int k = tid + (it0 + i) * T;
+                        if (k <= M / 2) {
+                            Z[PAD<PF>(k)] = zero;
+                            Z[PAD<PF>((N - k) & (N - 1))] = zero;
+                            Z[PAD<PF>(M - k)] = zero;
+                            Z[PAD<PF>(M + k)] = zero;
+                            if (!fold) {
+                                Cz[PAD<PH>(k)] = zero;
+                                if (k > 0) Cz[PAD<PH>(M - k)] = zero;
+                            }
+                        }
+                    }
+                    continue;
                 }
 #pragma unroll
                 for (int i = 0; i < CH; i++) {
-                    const int k = tid + (it0 + i) * T;
-                    if (k <= M / 2) {
-                        const int k2 = M - k;
-                        const int km = (N - k) & (N - 1);
-                        const float2 a1 = Z[PAD<PF>(k)], b1 = Z[PAD<PF>(km)];
-                        const float2 a2 = Z[PAD<PF>(k2)], b2 = Z[PAD<PF>(M + k)];
-                        float2 c1, y1, y1m, c2, y2, y2m;
+                    const int kq = tid + (it0 + i) * T;
+                    const bool live = kq <= M / 2;
+                    const int k = min(kq, M / 2);        // surplus threads recompute bin M/2 and store nothing
+                    const int k2 = M - k;
+                    const int km = (N - k) & (N - 1);
+                    const float2 a1 = Z[PAD<PF>(k)], b1 = Z[PAD<PF>(km)];
+                    const float2 a2 = Z[PAD<PF>(k2)], b2 = Z[PAD<PF>(M + k)];
+                    float2 c1, y1, y1m, c2, y2, y2m;
+                    if constexpr (MODE == MODE_MERGED) {
                         mask_bin_merged(a1, b1, g1[i], gain + k, b.n_gains, b.gain_stride, y1, y1m, c1);
                         mask_bin_merged(a2, b2, g2[i], gain + k2, b.n_gains, b.gain_stride, y2, y2m, c2);
-                        if (fold) {
-                            // (Ls + C/2) + i (Rs + C/2) = (Ls + i Rs) + (1+i) C/2: the fold-down is linear, so
-                            // it is taken here and the centre needs no transform of its own
-                            y1 = make_float2(y1.x + 0.5f * (c1.x - c1.y), y1.y + 0.5f * (c1.x + c1.y));
-                            y1m = make_float2(y1m.x + 0.5f * (c1.x + c1.y), y1m.y + 0.5f * (c1.x - c1.y));
-                            y2 = make_float2(y2.x + 0.5f * (c2.x - c2.y), y2.y + 0.5f * (c2.x + c2.y));
-                            y2m = make_float2(y2m.x + 0.5f * (c2.x + c2.y), y2m.y + 0.5f * (c2.x - c2.y));
-                        }
+                    } else {
+                        mask_bin(a1, b1, g1[i], y1, y1m, c1);
+                        mask_bin(a2, b2, g2[i], y2, y2m, c2);
+                    }
+                    if (fold) {
+                        // (Ls + C/2) + i (Rs + C/2) = (Ls + i Rs) + (1+i) C/2: the fold-down is linear, so
+                        // it is taken here and the centre needs no transform of its own
+                        y1 = make_float2(y1.x + 0.5f * (c1.x - c1.y), y1.y + 0.5f * (c1.x + c1.y));
+                        y1m = make_float2(y1m.x + 0.5f * (c1.x + c1.y), y1m.y + 0.5f * (c1.x - c1.y));
+                        y2 = make_float2(y2.x + 0.5f * (c2.x - c2.y), y2.y + 0.5f * (c2.x + c2.y));
+                        y2m = make_float2(y2m.x + 0.5f * (c2.x + c2.y), y2m.y + 0.5f * (c2.x - c2.y));
+                    }
+                    if (live) {
                         Z[PAD<PF>(k)] = y1;
                         Z[PAD<PF>(km)] = y1m;
                         Z[PAD<PF>(k2)] = y2;
                         Z[PAD<PF>(M + k)] = y2m;
-                        if (!fold) {
-                            // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);
-                            // IFFT_M(z)[m] = c[2m] + i c[2m+1]
-                            const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
-                            const float2 B = make_float2(c1.x - c2.x, c1.y + c2.y);
-                            const float2 D = cmul(B, make_float2(wp[i].x, -wp[i].y));
+                    }
+                    if (!fold) {
+                        // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);
+                        // IFFT_M(z)[m] = c[2m] + i c[2m+1]
+                        const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
+                        const float2 B = make_float2(c1.x - c2.x, c1.y + c2.y);
+                        const float2 D = cmul(B, make_float2(wp[i].x, -wp[i].y));
+                        if (live) {
                             Cz[PAD<PH>(k)] = make_float2(A.x - D.y, A.y + D.x);
                             if (k > 0) Cz[PAD<PH>(M - k)] = make_float2(A.x + D.y, D.x - A.y);
                         }
@@ -426,12 +464,17 @@ UPMIX_ROW_CFG(4096, UPMIX_ROWPLAN_4096)
 // mirror images of each other (bin k <-> N-k), so the CTA holds both rows of both frames, finishes
 // the forward transform along the rows, applies split/gain/mask, and starts the inverse transform
 // (rows) of Ls+iRs for each frame and of C(even frame) + i*C(odd frame).
-template <int N2>
+//
+// PRUNED: every non-zero gain of the pipeline sits below bin 16*ROW_K (BandDev::max_bin; true for every
+// band the dynamic-resolution rule sizes above 8192, whose pass band ends near bin 430).  Then only
+// the first and last ROW_K points of each row carry signal: the forward row transforms compute just
+// those, the mask runs over 2*ROW_K mirror pairs per CTA instead of N2, and the inverse row transforms
+// start from those inputs alone (fft_rows_fwd_pruned / fft_rows_inv_pruned).
+template <int N2, bool PRUNED>
 __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b, const WaveArgs w) {
     constexpr int T = RowCfg<N2>::T;
     constexpr int PL = RowCfg<N2>::PLAN;
     constexpr int RS = PADSZ<PL>();
-    constexpr int N = COL_R * N2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* S = reinterpret_cast<float2*>(smem_raw);   // 6 rows: f0a f0b f1a f1b ca cb
     const int tid = threadIdx.x;
@@ -457,52 +500,81 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 #endif
         };
         float2* buf = S + 2 * g * RS;
-        auto st = make_store([&](int row, int k, float2 v, NoAux) { buf[row * RS + PAD<PL>(k)] = v; });
-        fft_smem<PL, -1, T, 2, false>(buf, tid, tw, ld, st);
+        if constexpr (PRUNED) {
+            fft_rows_fwd_pruned<PL, T>(buf, tid, tw, ld);
+        } else {
+            auto st = make_store([&](int row, int k, float2 v, NoAux) { buf[row * RS + PAD<PL>(k)] = v; });
+            fft_smem<PL, -1, T, 2, false>(buf, tid, tw, ld, st);
+        }
     }
 
-    // split / gain / mask over mirror pairs
-    const int n_items = pr == 0 ? N2 + 1 : N2;
-    {
+    // split / gain / mask over mirror pairs: item -> (lo, hi) = shared-memory slots of bin and N - bin
+    auto item_slots = [&](int it, int& lo, int& hi, int& bin) {
+        int lo_row, lo_idx, hi_row, hi_idx;
+        if constexpr (PRUNED) {
+            // items [0, K): pair starts in the first row; [K, 2K): in the second row
+            const int j = it & (ROW_K - 1);
+            const bool second = it >= ROW_K;
+            if (pr != 0) {
+                lo_row = second ? 1 : 0; lo_idx = j; hi_row = second ? 0 : 1; hi_idx = N2 - 1 - j;
+                bin = (second ? kb : ka) + COL_R * j;
+            } else if (!second) {             // row 0: bin 16*j <-> 16*(N2-j)
+                lo_row = 0; lo_idx = j; hi_row = 0; hi_idx = (N2 - j) & (N2 - 1); bin = COL_R * j;
+            } else {                          // row 8: bin 8+16*j <-> 8+16*(N2-1-j)
+                lo_row = 1; lo_idx = j; hi_row = 1; hi_idx = N2 - 1 - j; bin = COL_R / 2 + COL_R * j;
+            }
+        } else if (pr != 0) {
+            const int k2 = it;
+            if (k2 < N2 / 2) { lo_row = 0; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = ka + COL_R * k2; }
+            else { lo_row = 1; lo_idx = N2 - 1 - k2; hi_row = 0; hi_idx = k2; bin = kb + COL_R * (N2 - 1 - k2); }
+        } else if (it <= N2 / 2) {            // row 0: bin 16*k2 <-> 16*(N2-k2)
+            lo_row = 0; lo_idx = it; hi_row = 0; hi_idx = (N2 - it) & (N2 - 1); bin = COL_R * it;
+        } else {                              // row 8: bin 8+16*k2 <-> 8+16*(N2-1-k2)
+            const int k2 = it - (N2 / 2 + 1);
+            lo_row = 1; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = COL_R / 2 + COL_R * k2;
+        }
+        lo = lo_row * RS + PAD<PL>(lo_idx);
+        hi = hi_row * RS + PAD<PL>(hi_idx);
+    };
+    auto mask_item = [&](int lo, int hi, int bin, float g) {
+        float2 c[2];
+#pragma unroll
+        for (int fr = 0; fr < 2; fr++) {
+            float2* buf = S + 2 * fr * RS;
+            float2 ylo, yhi;
+            mask_bin_merged(buf[lo], buf[hi], g, gain + bin, b.n_gains, b.gain_stride, ylo, yhi, c[fr]);
+            buf[lo] = ylo;
+            buf[hi] = yhi;
+        }
+        float2* cb = S + 4 * RS;
+        cb[lo] = make_float2(c[0].x - c[1].y, c[0].y + c[1].x);
+        cb[hi] = make_float2(c[0].x + c[1].y, c[1].x - c[0].y);
+    };
+    if constexpr (PRUNED) {
+        if (tid < 2 * ROW_K) {
+            int lo, hi, bin;
+            item_slots(tid, lo, hi, bin);
+            mask_item(lo, hi, bin, __ldg(gain + bin));
+        } else if (tid == 2 * ROW_K && pr == 0) {
+            // row 0, point N2-K: the mirror of bin 16*K, which has no gain -- not covered by an item, but
+            // the pruned inverse reads it
+            const int z = PAD<PL>(N2 - ROW_K);
+            S[z] = S[2 * RS + z] = S[4 * RS + z] = make_float2(0.f, 0.f);
+        }
+    } else {
+        const int n_items = pr == 0 ? N2 + 1 : N2;
         constexpr int ITM = (N2 + 1 + T - 1) / T;
         int lo_a[ITM], hi_a[ITM], bin_a[ITM];
         float g_a[ITM];
 #pragma unroll
         for (int i = 0; i < ITM; i++) {                 // index arithmetic and gain loads first
-            const int it = min(tid + i * T, n_items - 1);
-            int lo_row, lo_idx, hi_row, hi_idx, bin;
-            if (pr != 0) {
-                const int k2 = it;
-                if (k2 < N2 / 2) { lo_row = 0; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = ka + COL_R * k2; }
-                else { lo_row = 1; lo_idx = N2 - 1 - k2; hi_row = 0; hi_idx = k2; bin = kb + COL_R * (N2 - 1 - k2); }
-            } else if (it <= N2 / 2) {          // row 0: bin 16*k2 <-> 16*(N2-k2)
-                lo_row = 0; lo_idx = it; hi_row = 0; hi_idx = (N2 - it) & (N2 - 1); bin = COL_R * it;
-            } else {                            // row 8: bin 8+16*k2 <-> 8+16*(N2-1-k2)
-                const int k2 = it - (N2 / 2 + 1);
-                lo_row = 1; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = COL_R / 2 + COL_R * k2;
-            }
-            lo_a[i] = lo_row * RS + PAD<PL>(lo_idx);
-            hi_a[i] = hi_row * RS + PAD<PL>(hi_idx);
-            g_a[i] = __ldg(gain + bin);
-            bin_a[i] = bin;
+            item_slots(min(tid + i * T, n_items - 1), lo_a[i], hi_a[i], bin_a[i]);
+            g_a[i] = __ldg(gain + bin_a[i]);
         }
 #pragma unroll
         for (int i = 0; i < ITM; i++) {
             if (tid + i * T >= n_items) break;
-            const int lo = lo_a[i], hi = hi_a[i];
-            const float g = g_a[i];
-            float2 c[2];
-#pragma unroll
-            for (int fr = 0; fr < 2; fr++) {
-                float2* buf = S + 2 * fr * RS;
-                float2 ylo, yhi;
-                mask_bin_merged(buf[lo], buf[hi], g, gain + bin_a[i], b.n_gains, b.gain_stride, ylo, yhi, c[fr]);
-                buf[lo] = ylo;
-                buf[hi] = yhi;
-            }
-            float2* cb = S + 4 * RS;
-            cb[lo] = make_float2(c[0].x - c[1].y, c[0].y + c[1].x);
-            cb[hi] = make_float2(c[0].x + c[1].y, c[1].x - c[0].y);
+            mask_item(lo_a[i], hi_a[i], bin_a[i], g_a[i]);
         }
     }
     __syncthreads();
@@ -511,7 +583,6 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 #pragma unroll
     for (int g = 0; g < 3; g++) {
         float2* buf = S + 2 * g * RS;
-        auto ld = [&](int row, int n, int, int) -> float2 { return buf[row * RS + PAD<PL>(n)]; };
         float2* dst = g < 2 ? w.b1 + (fbase + (long long)g * COL_R) * N2
                             : w.b2 + (((long long)track * (w.n_frames / 2) + fp) * COL_R) * N2;
 #if UPMIX_TW_IN_ROW
@@ -523,9 +594,13 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 #else
         auto st = make_store([&](int row, int n, float2 v, NoAux) { dst[(long long)(row ? kb : ka) * N2 + n] = v; });
 #endif
-        fft_smem<PL, +1, T, 2, true>(buf, tid, tw, ld, st);
+        if constexpr (PRUNED) {
+            fft_rows_inv_pruned<PL, T>(buf, tid, tw, st);
+        } else {
+            auto ld = [&](int row, int n, int, int) -> float2 { return buf[row * RS + PAD<PL>(n)]; };
+            fft_smem<PL, +1, T, 2, true>(buf, tid, tw, ld, st);
+        }
     }
-    (void)N;
 }
 
 // K3: one thread per (column n2, run of hops, track).  For every frame pair of the run (plus the
@@ -892,20 +967,26 @@ unsigned long long launch_count(bool reset) {
     if (reset) g_launches = 0;
     return v;
 }
-template <int N>
-static cudaError_t launch_fused_n(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st) {
+template <int N, int MODE>
+static cudaError_t launch_fused_nm(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st) {
     static bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(band_fused_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(band_fused_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              FusedCfg<N>::SMEM);
         if (e != cudaSuccess) return e;
         attr_done[dev & 63] = true;
     }
-    band_fused_kernel<N><<<dim3(n_runs, n_tracks), FusedCfg<N>::T, FusedCfg<N>::SMEM, st>>>(b, a);
+    band_fused_kernel<N, MODE><<<dim3(n_runs, n_tracks), FusedCfg<N>::T, FusedCfg<N>::SMEM, st>>>(b, a);
     g_launches++;
     return cudaGetLastError();
+}
+template <int N>
+static cudaError_t launch_fused_n(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st) {
+    if (b.n_gains > 1) return launch_fused_nm<N, MODE_MERGED>(b, a, n_runs, n_tracks, st);
+    return a.fold ? launch_fused_nm<N, MODE_FOLD>(b, a, n_runs, n_tracks, st)
+                  : launch_fused_nm<N, MODE_PLAIN>(b, a, n_runs, n_tracks, st);
 }
 
 cudaError_t launch_band_fused(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st) {
@@ -972,20 +1053,27 @@ cudaError_t launch_col_fwd(const BandDev& b, const SegArgs& a, const WaveArgs& w
     return cudaGetLastError();
 }
 
-template <int N2>
-static cudaError_t launch_row_n(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
+template <int N2, bool PRUNED>
+static cudaError_t launch_row_np(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
     static bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(row_mask_kernel<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(row_mask_kernel<N2, PRUNED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              RowCfg<N2>::SMEM);
         if (e != cudaSuccess) return e;
         attr_done[dev & 63] = true;
     }
-    row_mask_kernel<N2><<<dim3(COL_R / 2, w.n_frames / 2, n_tracks), RowCfg<N2>::T, RowCfg<N2>::SMEM, st>>>(b, w);
+    row_mask_kernel<N2, PRUNED><<<dim3(COL_R / 2, w.n_frames / 2, n_tracks), RowCfg<N2>::T, RowCfg<N2>::SMEM, st>>>(b, w);
     g_launches++;
     return cudaGetLastError();
+}
+// The pruned row kernel needs every non-zero gain below bin 16*ROW_K (UPMIX_ROW_PRUNE=0 forces the full one).
+template <int N2>
+static cudaError_t launch_row_n(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
+    static const bool allow = [] { const char* e = getenv("UPMIX_ROW_PRUNE"); return !(e && atoi(e) == 0); }();
+    if (allow && b.max_bin < COL_R * ROW_K) return launch_row_np<N2, true>(b, w, n_tracks, st);
+    return launch_row_np<N2, false>(b, w, n_tracks, st);
 }
 
 cudaError_t launch_row_mask(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {

@@ -23,6 +23,7 @@ struct BandDev {
                                // pipeline (same n_fft/hop/windows); per bin the non-zero gains come first
     int n_gains;
     int gain_stride;           // >= n_fft/2+1
+    int max_bin;               // highest bin with a non-zero gain in any of the merged bands (-1: none)
     const float2* tw_fft;      // per-pass twiddles (fft_device.cuh layout) of the n_fft-point transform
                                // (fused path) or of the n_fft/16-point row transform (large path)
     const float2* tw_half;     // per-pass twiddles of the n_fft/2-point transform (fused path)
