@@ -299,8 +299,10 @@ class Plan:
         track is cut into time segments (multiples of the largest hop); input chunks go up on one
         stream, each segment is processed as soon as its halo'd input has landed
         (upmix_process_segment: bit-identical to one whole-track call) and its outputs come down on a
-        third stream, so H2D, kernels and D2H overlap.  segment_seconds = 0 picks up to 8 segments of
-        at least two minutes (short segments under-fill the GPU).  Returns pinned CPU tensors,
+        third stream, so H2D, kernels and D2H overlap.  segment_seconds = 0 picks segments of about 90 s
+        (measured on B200, 1-hour track, profiles/e2e_sweep.py: 450 s segments 48.2 ms, 120 s 43.1 ms,
+        60 s 42.9 ms, 30 s 45.4 ms -- the device-to-host copy alone takes 38.9 ms; shorter segments let
+        it start earlier, very short ones under-fill the GPU).  Returns pinned CPU tensors,
         overwritten by the next call on this plan."""
         torch = _torch()
         if L.dtype != torch.float32 or R.dtype != torch.float32 or L.dim() != 1 or L.shape != R.shape:
@@ -318,7 +320,7 @@ class Plan:
         main = torch.cuda.current_stream(dev)
         align = max(self.hops)
         if segment_seconds <= 0:
-            n_seg = max(1, min(8, int(n / (120.0 * sample_rate))))
+            n_seg = max(1, min(64, int(round(n / (90.0 * sample_rate)))))
             seg = -(-n // n_seg)
         else:
             seg = int(segment_seconds * sample_rate)
