@@ -334,16 +334,18 @@ __host__ __device__ constexpr unsigned inv_p1_in_mask(int n2, int K) {
     return m;
 }
 
-// Forward transform of two rows when only outputs [0,K) and [N2-K,N2) are needed (they alone are
-// written to buf; everything else in buf is left undefined).  PLAN = {16, 16, R2}.  ld as in fft_smem.
-template <int PLAN, int T, class Ld>
-__device__ __forceinline__ void fft_rows_fwd_pruned(float2* buf, int tid, const float2* __restrict__ tw, Ld ld) {
+// Forward transform of ROWS rows when only outputs [0,K) and [N2-K,N2) are needed.  They are handed to
+// out(row, idx, value), idx in [0, 2K): idx < K is point idx, idx >= K is point N2 - 2K + idx; buf is
+// scratch.  PLAN = {16, 16, R2}.  ld as in fft_smem.  Ends with a __syncthreads().
+template <int PLAN, int T, int ROWS, class Ld, class Out>
+__device__ __forceinline__ void fft_rows_fwd_pruned(float2* buf, int tid, const float2* __restrict__ tw, Ld ld, Out out) {
     constexpr int N = fft_size(PLAN), RS = PADSZ<PLAN>(), K = ROW_K;
     static_assert(fft_num_passes(PLAN) == 3 && fft_radix(PLAN, 0) == 16 && fft_radix(PLAN, 1) == 16, "row plans are {16,16,R}");
+    static_assert(T >= ROWS * 2 * K, "the pruned passes need 2K threads per row");
     auto none = make_store([](int, int, float2, NoAux) {});
-    stockham_pass<PLAN, 0, -1, T, 2, false, Ld, decltype(none)>(buf, tid, tw, ld, none);
+    stockham_pass<PLAN, 0, -1, T, ROWS, false, Ld, decltype(none)>(buf, tid, tw, ld, none);
     {   // pass 1: full butterflies, only the consumed outputs are stored
-        constexpr int R = 16, NS = 16, NB = N / R, TOTAL = 2 * NB, IT = (TOTAL + T - 1) / T;
+        constexpr int R = 16, NS = 16, NB = N / R, TOTAL = ROWS * NB, IT = (TOTAL + T - 1) / T;
         constexpr unsigned OUT = fwd_p1_out_mask(K);
         constexpr int LD_STR = NB + NB / 16, ST_STR = NS + NS / 16;
         float2 v[IT][R], w[IT][R];
@@ -351,7 +353,7 @@ __device__ __forceinline__ void fft_rows_fwd_pruned(float2* buf, int tid, const 
         for (int it = 0; it < IT; it++) {
             const int jj = tid + it * T;
             if (TOTAL % T == 0 || jj < TOTAL) {
-                const int row = jj / NB, j = jj - row * NB, k = j & (NS - 1);
+                const int row = ROWS == 1 ? 0 : jj / NB, j = jj - row * NB, k = j & (NS - 1);
                 const float2* __restrict__ twp = tw + fft_tw_offset(PLAN, 1) + k;
 #pragma unroll
                 for (int r = 1; r < R; r++) w[it][r] = __ldg(twp + (r - 1) * NS);
@@ -365,7 +367,7 @@ __device__ __forceinline__ void fft_rows_fwd_pruned(float2* buf, int tid, const 
         for (int it = 0; it < IT; it++) {
             const int jj = tid + it * T;
             if (TOTAL % T == 0 || jj < TOTAL) {
-                const int row = jj / NB, j = jj - row * NB, k = j & (NS - 1);
+                const int row = ROWS == 1 ? 0 : jj / NB, j = jj - row * NB, k = j & (NS - 1);
 #pragma unroll
                 for (int r = 1; r < R; r++) v[it][r] = cmul(v[it][r], w[it][r]);
                 Dft<R, -1>::run(v[it]);
@@ -381,56 +383,40 @@ __device__ __forceinline__ void fft_rows_fwd_pruned(float2* buf, int tid, const 
         constexpr int R = fft_radix(PLAN, 2), NS = 256, NB = N / R;
         static_assert(NB == 256, "pass 2 of a row plan has 256 butterflies");
         constexpr int LD_STR = NB + NB / 16;
-        const bool act = tid < 4 * K;                       // 2 rows x 2K butterflies
+        const bool act = tid < ROWS * 2 * K;
         const int row = tid / (2 * K), a = tid - row * 2 * K;
-        const bool low = a < K;
+        const bool low = a < K;                             // warp-uniform: K is a multiple of 32
         const int j = low ? a : NS - 2 * K + a;
-        float2 v[R], w[R];
         if (act) {
+            float2 v[R], w[R];
             const float2* __restrict__ twp = tw + fft_tw_offset(PLAN, 2) + j;
 #pragma unroll
             for (int r = 1; r < R; r++) w[r] = __ldg(twp + (r - 1) * NS);
             const float2* __restrict__ src = buf + row * RS + PAD<PLAN>(j);
 #pragma unroll
             for (int r = 0; r < R; r++) v[r] = src[r * LD_STR];
-        }
-        __syncthreads();
-        if (act) {
 #pragma unroll
             for (int r = 1; r < R; r++) v[r] = cmul(v[r], w[r]);
-            if (low) {                                      // warp-uniform: K is a multiple of 32
-                float2 u[R];
-#pragma unroll
-                for (int r = 0; r < R; r++) u[r] = v[r];
-                Dft<R, -1>::run(u);
-                buf[row * RS + PAD<PLAN>(j)] = u[0];
-            } else {
-                float2 u[R];
-#pragma unroll
-                for (int r = 0; r < R; r++) u[r] = v[r];
-                Dft<R, -1>::run(u);
-                buf[row * RS + PAD<PLAN>(j + (R - 1) * NS)] = u[R - 1];
-            }
+            Dft<R, -1>::run(v);                             // the compiler keeps only the output used
+            out(row, a, low ? v[0] : v[R - 1]);
         }
         __syncthreads();
     }
 }
 
-// Inverse transform of two rows whose only non-zero inputs are [0,K) and [N2-K,N2) (the rest of buf is
-// never read).  st as in fft_smem (last pass output functor).
-template <int PLAN, int T, class St>
-__device__ __forceinline__ void fft_rows_inv_pruned(float2* buf, int tid, const float2* __restrict__ tw, St st) {
+// Inverse transform of ROWS rows whose only non-zero inputs are points [0,K) and [N2-K,N2), supplied by
+// in(row, idx) with idx as in fft_rows_fwd_pruned.  st as in fft_smem (last pass output functor).
+template <int PLAN, int T, int ROWS, class In, class St>
+__device__ __forceinline__ void fft_rows_inv_pruned(float2* buf, int tid, const float2* __restrict__ tw, In in, St st) {
     constexpr int N = fft_size(PLAN), RS = PADSZ<PLAN>(), K = ROW_K;
-    {   // pass 0: 2K butterflies per row, one non-zero input each
+    static_assert(T >= ROWS * 2 * K, "the pruned passes need 2K threads per row");
+    {   // pass 0: 2K butterflies per row, one non-zero input each; nothing of buf is read
         constexpr int R = 16, NB = N / R;
-        const bool act = tid < 4 * K;
-        const int row = tid / (2 * K), a = tid - row * 2 * K;
-        const bool low = a < K;
-        const int j = low ? a : NB - 2 * K + a;
-        float2 x = make_float2(0.f, 0.f);
-        if (act) x = buf[row * RS + PAD<PLAN>(low ? j : j + (R - 1) * NB)];
-        __syncthreads();
-        if (act) {
+        if (tid < ROWS * 2 * K) {
+            const int row = tid / (2 * K), a = tid - row * 2 * K;
+            const bool low = a < K;
+            const int j = low ? a : NB - 2 * K + a;
+            const float2 x = in(row, a);
             float2 v[R];
             float2* __restrict__ dst = buf + row * RS + PAD<PLAN>(j * R);      // NS = 1: outputs j*16 + r, contiguous
             if (low) {
@@ -446,7 +432,7 @@ __device__ __forceinline__ void fft_rows_inv_pruned(float2* buf, int tid, const 
         __syncthreads();
     }
     {   // pass 1: every butterfly, but only the inputs that pass 0 can have filled
-        constexpr int R = 16, NS = 16, NB = N / R, TOTAL = 2 * NB, IT = (TOTAL + T - 1) / T;
+        constexpr int R = 16, NS = 16, NB = N / R, TOTAL = ROWS * NB, IT = (TOTAL + T - 1) / T;
         constexpr unsigned NZ = inv_p1_in_mask(N, K);
         constexpr int LD_STR = NB + NB / 16, ST_STR = NS + NS / 16;
         float2 v[IT][R], w[IT][R];
@@ -454,7 +440,7 @@ __device__ __forceinline__ void fft_rows_inv_pruned(float2* buf, int tid, const 
         for (int it = 0; it < IT; it++) {
             const int jj = tid + it * T;
             if (TOTAL % T == 0 || jj < TOTAL) {
-                const int row = jj / NB, j = jj - row * NB, k = j & (NS - 1);
+                const int row = ROWS == 1 ? 0 : jj / NB, j = jj - row * NB, k = j & (NS - 1);
                 const float2* __restrict__ twp = tw + fft_tw_offset(PLAN, 1) + k;
                 const float2* __restrict__ src = buf + row * RS + PAD<PLAN>(j);
 #pragma unroll
@@ -470,7 +456,7 @@ __device__ __forceinline__ void fft_rows_inv_pruned(float2* buf, int tid, const 
         for (int it = 0; it < IT; it++) {
             const int jj = tid + it * T;
             if (TOTAL % T == 0 || jj < TOTAL) {
-                const int row = jj / NB, j = jj - row * NB, k = j & (NS - 1);
+                const int row = ROWS == 1 ? 0 : jj / NB, j = jj - row * NB, k = j & (NS - 1);
 #pragma unroll
                 for (int r = 1; r < R; r++)
                     if ((NZ >> r) & 1u) v[it][r] = cmul(v[it][r], make_float2(w[it][r].x, -w[it][r].y));
@@ -483,7 +469,7 @@ __device__ __forceinline__ void fft_rows_inv_pruned(float2* buf, int tid, const 
         __syncthreads();
     }
     auto nold = [](int, int, int, int) -> float2 { return make_float2(0.f, 0.f); };
-    stockham_pass<PLAN, 2, +1, T, 2, true, decltype(nold), St>(buf, tid, tw, nold, st);
+    stockham_pass<PLAN, 2, +1, T, ROWS, true, decltype(nold), St>(buf, tid, tw, nold, st);
 }
 
 // ---------------------------------------------------------------------------------------------

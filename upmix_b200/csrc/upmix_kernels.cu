@@ -464,13 +464,7 @@ UPMIX_ROW_CFG(4096, UPMIX_ROWPLAN_4096)
 // mirror images of each other (bin k <-> N-k), so the CTA holds both rows of both frames, finishes
 // the forward transform along the rows, applies split/gain/mask, and starts the inverse transform
 // (rows) of Ls+iRs for each frame and of C(even frame) + i*C(odd frame).
-//
-// PRUNED: every non-zero gain of the pipeline sits below bin 16*ROW_K (BandDev::max_bin; true for every
-// band the dynamic-resolution rule sizes above 8192, whose pass band ends near bin 430).  Then only
-// the first and last ROW_K points of each row carry signal: the forward row transforms compute just
-// those, the mask runs over 2*ROW_K mirror pairs per CTA instead of N2, and the inverse row transforms
-// start from those inputs alone (fft_rows_fwd_pruned / fft_rows_inv_pruned).
-template <int N2, bool PRUNED>
+template <int N2>
 __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b, const WaveArgs w) {
     constexpr int T = RowCfg<N2>::T;
     constexpr int PL = RowCfg<N2>::PLAN;
@@ -500,81 +494,52 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 #endif
         };
         float2* buf = S + 2 * g * RS;
-        if constexpr (PRUNED) {
-            fft_rows_fwd_pruned<PL, T>(buf, tid, tw, ld);
-        } else {
-            auto st = make_store([&](int row, int k, float2 v, NoAux) { buf[row * RS + PAD<PL>(k)] = v; });
-            fft_smem<PL, -1, T, 2, false>(buf, tid, tw, ld, st);
-        }
+        auto st = make_store([&](int row, int k, float2 v, NoAux) { buf[row * RS + PAD<PL>(k)] = v; });
+        fft_smem<PL, -1, T, 2, false>(buf, tid, tw, ld, st);
     }
 
-    // split / gain / mask over mirror pairs: item -> (lo, hi) = shared-memory slots of bin and N - bin
-    auto item_slots = [&](int it, int& lo, int& hi, int& bin) {
-        int lo_row, lo_idx, hi_row, hi_idx;
-        if constexpr (PRUNED) {
-            // items [0, K): pair starts in the first row; [K, 2K): in the second row
-            const int j = it & (ROW_K - 1);
-            const bool second = it >= ROW_K;
-            if (pr != 0) {
-                lo_row = second ? 1 : 0; lo_idx = j; hi_row = second ? 0 : 1; hi_idx = N2 - 1 - j;
-                bin = (second ? kb : ka) + COL_R * j;
-            } else if (!second) {             // row 0: bin 16*j <-> 16*(N2-j)
-                lo_row = 0; lo_idx = j; hi_row = 0; hi_idx = (N2 - j) & (N2 - 1); bin = COL_R * j;
-            } else {                          // row 8: bin 8+16*j <-> 8+16*(N2-1-j)
-                lo_row = 1; lo_idx = j; hi_row = 1; hi_idx = N2 - 1 - j; bin = COL_R / 2 + COL_R * j;
-            }
-        } else if (pr != 0) {
-            const int k2 = it;
-            if (k2 < N2 / 2) { lo_row = 0; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = ka + COL_R * k2; }
-            else { lo_row = 1; lo_idx = N2 - 1 - k2; hi_row = 0; hi_idx = k2; bin = kb + COL_R * (N2 - 1 - k2); }
-        } else if (it <= N2 / 2) {            // row 0: bin 16*k2 <-> 16*(N2-k2)
-            lo_row = 0; lo_idx = it; hi_row = 0; hi_idx = (N2 - it) & (N2 - 1); bin = COL_R * it;
-        } else {                              // row 8: bin 8+16*k2 <-> 8+16*(N2-1-k2)
-            const int k2 = it - (N2 / 2 + 1);
-            lo_row = 1; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = COL_R / 2 + COL_R * k2;
-        }
-        lo = lo_row * RS + PAD<PL>(lo_idx);
-        hi = hi_row * RS + PAD<PL>(hi_idx);
-    };
-    auto mask_item = [&](int lo, int hi, int bin, float g) {
-        float2 c[2];
-#pragma unroll
-        for (int fr = 0; fr < 2; fr++) {
-            float2* buf = S + 2 * fr * RS;
-            float2 ylo, yhi;
-            mask_bin_merged(buf[lo], buf[hi], g, gain + bin, b.n_gains, b.gain_stride, ylo, yhi, c[fr]);
-            buf[lo] = ylo;
-            buf[hi] = yhi;
-        }
-        float2* cb = S + 4 * RS;
-        cb[lo] = make_float2(c[0].x - c[1].y, c[0].y + c[1].x);
-        cb[hi] = make_float2(c[0].x + c[1].y, c[1].x - c[0].y);
-    };
-    if constexpr (PRUNED) {
-        if (tid < 2 * ROW_K) {
-            int lo, hi, bin;
-            item_slots(tid, lo, hi, bin);
-            mask_item(lo, hi, bin, __ldg(gain + bin));
-        } else if (tid == 2 * ROW_K && pr == 0) {
-            // row 0, point N2-K: the mirror of bin 16*K, which has no gain -- not covered by an item, but
-            // the pruned inverse reads it
-            const int z = PAD<PL>(N2 - ROW_K);
-            S[z] = S[2 * RS + z] = S[4 * RS + z] = make_float2(0.f, 0.f);
-        }
-    } else {
-        const int n_items = pr == 0 ? N2 + 1 : N2;
+    // split / gain / mask over mirror pairs
+    const int n_items = pr == 0 ? N2 + 1 : N2;
+    {
         constexpr int ITM = (N2 + 1 + T - 1) / T;
         int lo_a[ITM], hi_a[ITM], bin_a[ITM];
         float g_a[ITM];
 #pragma unroll
         for (int i = 0; i < ITM; i++) {                 // index arithmetic and gain loads first
-            item_slots(min(tid + i * T, n_items - 1), lo_a[i], hi_a[i], bin_a[i]);
-            g_a[i] = __ldg(gain + bin_a[i]);
+            const int it = min(tid + i * T, n_items - 1);
+            int lo_row, lo_idx, hi_row, hi_idx, bin;
+            if (pr != 0) {
+                const int k2 = it;
+                if (k2 < N2 / 2) { lo_row = 0; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = ka + COL_R * k2; }
+                else { lo_row = 1; lo_idx = N2 - 1 - k2; hi_row = 0; hi_idx = k2; bin = kb + COL_R * (N2 - 1 - k2); }
+            } else if (it <= N2 / 2) {          // row 0: bin 16*k2 <-> 16*(N2-k2)
+                lo_row = 0; lo_idx = it; hi_row = 0; hi_idx = (N2 - it) & (N2 - 1); bin = COL_R * it;
+            } else {                            // row 8: bin 8+16*k2 <-> 8+16*(N2-1-k2)
+                const int k2 = it - (N2 / 2 + 1);
+                lo_row = 1; lo_idx = k2; hi_row = 1; hi_idx = N2 - 1 - k2; bin = COL_R / 2 + COL_R * k2;
+            }
+            lo_a[i] = lo_row * RS + PAD<PL>(lo_idx);
+            hi_a[i] = hi_row * RS + PAD<PL>(hi_idx);
+            g_a[i] = __ldg(gain + bin);
+            bin_a[i] = bin;
         }
 #pragma unroll
         for (int i = 0; i < ITM; i++) {
             if (tid + i * T >= n_items) break;
-            mask_item(lo_a[i], hi_a[i], bin_a[i], g_a[i]);
+            const int lo = lo_a[i], hi = hi_a[i];
+            const float g = g_a[i];
+            float2 c[2];
+#pragma unroll
+            for (int fr = 0; fr < 2; fr++) {
+                float2* buf = S + 2 * fr * RS;
+                float2 ylo, yhi;
+                mask_bin_merged(buf[lo], buf[hi], g, gain + bin_a[i], b.n_gains, b.gain_stride, ylo, yhi, c[fr]);
+                buf[lo] = ylo;
+                buf[hi] = yhi;
+            }
+            float2* cb = S + 4 * RS;
+            cb[lo] = make_float2(c[0].x - c[1].y, c[0].y + c[1].x);
+            cb[hi] = make_float2(c[0].x + c[1].y, c[1].x - c[0].y);
         }
     }
     __syncthreads();
@@ -583,6 +548,7 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 #pragma unroll
     for (int g = 0; g < 3; g++) {
         float2* buf = S + 2 * g * RS;
+        auto ld = [&](int row, int n, int, int) -> float2 { return buf[row * RS + PAD<PL>(n)]; };
         float2* dst = g < 2 ? w.b1 + (fbase + (long long)g * COL_R) * N2
                             : w.b2 + (((long long)track * (w.n_frames / 2) + fp) * COL_R) * N2;
 #if UPMIX_TW_IN_ROW
@@ -594,12 +560,101 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 #else
         auto st = make_store([&](int row, int n, float2 v, NoAux) { dst[(long long)(row ? kb : ka) * N2 + n] = v; });
 #endif
-        if constexpr (PRUNED) {
-            fft_rows_inv_pruned<PL, T>(buf, tid, tw, st);
-        } else {
-            auto ld = [&](int row, int n, int, int) -> float2 { return buf[row * RS + PAD<PL>(n)]; };
-            fft_smem<PL, +1, T, 2, true>(buf, tid, tw, ld, st);
+        fft_smem<PL, +1, T, 2, true>(buf, tid, tw, ld, st);
+    }
+}
+
+// K2, band-limited: every non-zero gain of the pipeline sits below bin 16*ROW_K (BandDev::max_bin; true
+// for every band the dynamic-resolution rule sizes above 8192, whose pass band ends near bin 430).
+// Then only the first and last ROW_K points of each row carry signal: the forward row transforms
+// compute just those (fft_rows_fwd_pruned) into a small spectrum array, the mask runs over 2*ROW_K
+// mirror pairs, and the inverse row transforms start from those inputs alone (fft_rows_inv_pruned).
+// With the six rows no longer resident the CTA needs one row of shared memory, so it transforms one row
+// at a time with half the threads and two (or more) CTAs share an SM: one computes while the other
+// waits for its rows to arrive from HBM.
+#ifndef UPMIX_ROWP_REGS
+#define UPMIX_ROWP_REGS 128       // register budget per thread: 65536 / (T * REGS) CTAs share an SM
+#endif
+template <int N2>
+__global__ void __launch_bounds__(N2 / 16, 65536 / (N2 / 16 * UPMIX_ROWP_REGS)) row_mask_pruned_kernel(const BandDev b, const WaveArgs w) {
+    constexpr int T = N2 / 16;
+    constexpr int PL = RowCfg<N2>::PLAN;
+    constexpr int RS = PADSZ<PL>();
+    constexpr int K = ROW_K;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* buf = reinterpret_cast<float2*>(smem_raw);             // one row being transformed
+    float2* spec = buf + RS;                                       // [3: f0 f1 c][2 rows][2K] band-limited spectra
+    const int tid = threadIdx.x;
+    const int pr = blockIdx.x;                          // 0: rows (0, 8) self-mirrored; p: rows (p, 16-p)
+    const int fp = blockIdx.y;
+    const int track = blockIdx.z;
+    const int ka = pr, kb = pr == 0 ? COL_R / 2 : COL_R - pr;
+    const long long fbase = ((long long)track * w.n_frames + 2 * fp) * COL_R;
+    const float2* __restrict__ A = w.a;
+    const float2* __restrict__ tw = b.tw_fft;
+    const float2* __restrict__ twc = b.tw_col;
+    const float* __restrict__ gain = b.gain;
+
+#pragma unroll 1
+    for (int s = 0; s < 4; s++) {                       // (frame, row) = (0,a) (0,b) (1,a) (1,b)
+        const int g = s >> 1, k1 = (s & 1) ? kb : ka;
+        const float2* __restrict__ src = A + (fbase + (long long)g * COL_R + k1) * N2;
+        const float2* __restrict__ twr = twc + k1 * N2;
+        auto ld = [&](int, int n, int, int) -> float2 { return cmul(src[n], __ldg(twr + n)); };   // * W_N^{k1 n}
+        float2* sp = spec + s * 2 * K;
+        auto out = [&](int, int idx, float2 v) { sp[idx] = v; };
+        fft_rows_fwd_pruned<PL, T, 1>(buf, tid, tw, ld, out);
+    }
+
+    // split / gain / mask over the 2K mirror pairs.  Slot idx < K is point idx of the row, idx >= K is
+    // point N2 - 2K + idx; items [0, K) start in the first row, [K, 2K) in the second.
+    if (tid < 2 * K) {
+        const int j = tid & (K - 1);
+        const bool second = tid >= K;
+        int lo, hi, bin;
+        if (pr != 0) {                  // bin k1 + 16 j  <->  (16 - k1) + 16 (N2 - 1 - j)
+            lo = (second ? 2 * K : 0) + j;
+            hi = (second ? 0 : 2 * K) + 2 * K - 1 - j;
+            bin = (second ? kb : ka) + COL_R * j;
+        } else if (!second) {           // row 0: bin 16 j <-> 16 (N2 - j)
+            lo = j;
+            hi = j == 0 ? 0 : 2 * K - j;
+            bin = COL_R * j;
+        } else {                        // row 8: bin 8 + 16 j <-> 8 + 16 (N2 - 1 - j)
+            lo = 2 * K + j;
+            hi = 2 * K + 2 * K - 1 - j;
+            bin = COL_R / 2 + COL_R * j;
         }
+        const float g = __ldg(gain + bin);
+        float2 c[2];
+#pragma unroll
+        for (int fr = 0; fr < 2; fr++) {
+            float2* sp = spec + fr * 4 * K;
+            float2 ylo, yhi;
+            mask_bin_merged(sp[lo], sp[hi], g, gain + bin, b.n_gains, b.gain_stride, ylo, yhi, c[fr]);
+            sp[lo] = ylo;
+            sp[hi] = yhi;
+        }
+        float2* cb = spec + 8 * K;
+        cb[lo] = make_float2(c[0].x - c[1].y, c[0].y + c[1].x);
+        cb[hi] = make_float2(c[0].x + c[1].y, c[1].x - c[0].y);
+        // row 0, point N2-K (slot K): the mirror of bin 16*K, which has no gain -- no item covers it, but
+        // the pruned inverse reads it
+        if (pr == 0 && tid == 0) spec[K] = spec[4 * K + K] = spec[8 * K + K] = make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int s = 0; s < 6; s++) {                       // (f0,a) (f0,b) (f1,a) (f1,b) (c,a) (c,b)
+        const int g = s >> 1, k1 = (s & 1) ? kb : ka;
+        float2* dst = (g < 2 ? w.b1 + (fbase + (long long)g * COL_R) * N2
+                             : w.b2 + (((long long)track * (w.n_frames / 2) + fp) * COL_R) * N2) + (long long)k1 * N2;
+        const float2* __restrict__ twr = twc + k1 * N2;
+        const float2* sp = spec + s * 2 * K;
+        auto in = [&](int, int idx) -> float2 { return sp[idx]; };
+        auto st = make_store([&](int, int n) -> float2 { return __ldg(twr + n); },
+                             [&](int, int n, float2 v, float2 t) { dst[n] = cmul(v, make_float2(t.x, -t.y)); });   // * conj W_N^{k1 n}
+        fft_rows_inv_pruned<PL, T, 1>(buf, tid, tw, in, st);
     }
 }
 
@@ -1053,18 +1108,33 @@ cudaError_t launch_col_fwd(const BandDev& b, const SegArgs& a, const WaveArgs& w
     return cudaGetLastError();
 }
 
-template <int N2, bool PRUNED>
-static cudaError_t launch_row_np(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
+template <int N2>
+static cudaError_t launch_row_full(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
     static bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(row_mask_kernel<N2, PRUNED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(row_mask_kernel<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              RowCfg<N2>::SMEM);
         if (e != cudaSuccess) return e;
         attr_done[dev & 63] = true;
     }
-    row_mask_kernel<N2, PRUNED><<<dim3(COL_R / 2, w.n_frames / 2, n_tracks), RowCfg<N2>::T, RowCfg<N2>::SMEM, st>>>(b, w);
+    row_mask_kernel<N2><<<dim3(COL_R / 2, w.n_frames / 2, n_tracks), RowCfg<N2>::T, RowCfg<N2>::SMEM, st>>>(b, w);
+    g_launches++;
+    return cudaGetLastError();
+}
+template <int N2>
+static cudaError_t launch_row_pruned(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
+    constexpr int SMEM = (PADSZ<RowCfg<N2>::PLAN>() + 12 * ROW_K) * (int)sizeof(float2);
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(row_mask_pruned_kernel<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done[dev & 63] = true;
+    }
+    row_mask_pruned_kernel<N2><<<dim3(COL_R / 2, w.n_frames / 2, n_tracks), N2 / 16, SMEM, st>>>(b, w);
     g_launches++;
     return cudaGetLastError();
 }
@@ -1072,8 +1142,8 @@ static cudaError_t launch_row_np(const BandDev& b, const WaveArgs& w, int n_trac
 template <int N2>
 static cudaError_t launch_row_n(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
     static const bool allow = [] { const char* e = getenv("UPMIX_ROW_PRUNE"); return !(e && atoi(e) == 0); }();
-    if (allow && b.max_bin < COL_R * ROW_K) return launch_row_np<N2, true>(b, w, n_tracks, st);
-    return launch_row_np<N2, false>(b, w, n_tracks, st);
+    if (allow && b.max_bin < COL_R * ROW_K) return launch_row_pruned<N2>(b, w, n_tracks, st);
+    return launch_row_full<N2>(b, w, n_tracks, st);
 }
 
 cudaError_t launch_row_mask(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
