@@ -513,3 +513,36 @@ def test_large_band_row_pruning_boundary(ce, n_fft, top_bin):
     got = e.process_all_blocks(L, R)
     peak = float(max(np.abs(L).max(), np.abs(R).max()))
     assert_parity(ref, got, peak, what=f"N={n_fft} top_bin={top_bin}")
+
+
+def test_direct_band_sum_is_identical_to_staged(ce, monkeypatch):
+    """The two ways of summing the bands (per-band slots + band_sum_kernel for short inputs, pipelines
+    adding straight into the outputs for long ones) do the same float32 additions in the same order:
+    Ls/C/Rs, fold-down with and without a four-step band, merged bands, track batches, time shards."""
+    import torch
+    sr = 48000
+    n = 3 * sr + 777
+    L, R = uo.synth_stereo(n, 31, stress=True)
+    dl, dr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    Ls = torch.stack([dl, dr, dl.flip(0)])
+    Rs = torch.stack([dr, dl, dr * 0.5])
+    cases = [([0, 200, 2000], 65536), ([0, 30, 120, 480, 1920, 7680], 65536), ([0, 300, 3000], 16384),
+             ([0, 500, 2000, 8000], 8192)]
+    for edges, max_block in cases:
+        ext = quiet(ce.chain_bands, edges, 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=max_block)
+        for fold in (False, True):
+            from upmix_b200 import _native
+            plan = ce.plan_for(ext, _native.OUT_FOLD if fold else _native.OUT_LSCRS)
+            res = {}
+            for mode, thr in (("staged", str(1 << 60)), ("direct", "1")):
+                monkeypatch.setenv("UPMIX_DIRECT_MIN", thr)
+                whole = [t.clone() for t in plan.process(dl, dr)]
+                batch = [t.clone() for t in plan.process(Ls, Rs)]
+                a, b = 16384 * 3, 16384 * 6 + 1234
+                lo, hi = max(0, a - plan.halo), min(n, b + plan.halo)
+                seg = [t.clone() for t in plan.process_segment(dl[lo:hi].contiguous(), dr[lo:hi].contiguous(), lo, n, a, b)]
+                for w, s in zip(whole, seg):
+                    assert torch.equal(w[a:b], s), (edges, fold, mode)
+                res[mode] = whole + batch
+            for x, y in zip(res["staged"], res["direct"]):
+                assert torch.equal(x, y), (edges, fold)

@@ -94,10 +94,24 @@ struct Layout {
     int64_t total = 0;
 };
 
-Layout make_layout(const UpmixPlan* p, int64_t seg_len, int n_tracks) {
+// Two ways to sum the bands (center_extraction.py:503-511), same float32 additions in the same order:
+//  * staged: every pipeline writes its C/Ls/Rs to a workspace slot, band_sum_kernel adds the slots.  The
+//    pipelines are independent until then and run on the plan's own streams -- best for short inputs
+//    (block streaming, a few seconds of audio), where launch gaps dominate.
+//  * direct: the pipelines run one after the other and add their finished samples straight into the
+//    caller's outputs (the first one stores).  No per-band slots (12 bytes per sample and band, written
+//    and read again), no band-sum pass: 84 -> 60 bytes of HBM traffic per sample for three bands, and
+//    the workspace shrinks to the four-step scratch.  Used from UPMIX_DIRECT_MIN samples up.
+bool direct_sum(int64_t seg_len, int n_tracks) {
+    int64_t min_samples = 4LL << 20;
+    if (const char* ev = getenv("UPMIX_DIRECT_MIN")) min_samples = atoll(ev);
+    return seg_len * (int64_t)n_tracks >= min_samples;
+}
+
+Layout make_layout(const UpmixPlan* p, int64_t seg_len, int n_tracks, bool staged) {
     Layout l;
     l.ws_seg = round_up(std::max<int64_t>(seg_len, 1), 64);
-    l.band_out_bytes = round_up((int64_t)p->bands.size() * 3 * n_tracks * l.ws_seg * (int64_t)sizeof(float), 256);
+    l.band_out_bytes = staged ? round_up((int64_t)p->bands.size() * 3 * n_tracks * l.ws_seg * (int64_t)sizeof(float), 256) : 0;
     l.total = l.band_out_bytes;
     if (p->max_large_n) {
         int64_t hop_min = INT64_MAX;
@@ -132,9 +146,12 @@ int pick_hops_per_run(const UpmixPlan* p, int n_fft, int64_t total_hops, int n_t
 int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_begin, int64_t in_end,
                 int64_t n_total, int64_t seg_begin, int64_t seg_end, int n_tracks, int64_t in_stride, float* out_c,
                 float* out_l, float* out_r, int64_t out_stride, void* workspace, int64_t workspace_bytes,
-                float* const* band_state, cudaStream_t st) {
+                float* const* band_state, cudaStream_t st, bool force_direct = false) {
     const int64_t seg_len = seg_end - seg_begin;
-    const Layout lay = make_layout(p, seg_len, n_tracks);
+    const int64_t prod_end = std::min(seg_end, n_total);      // nothing is produced past the end of the track
+    const bool direct = seg_begin >= 0 && prod_end == seg_end &&
+                        (force_direct || (band_state == nullptr && direct_sum(seg_len, n_tracks)));
+    const Layout lay = make_layout(p, seg_len, n_tracks, !direct);
     if (workspace_bytes < lay.total)
         return fail(UPMIX_E_WORKSPACE, "workspace too small: %lld bytes given, %lld needed", (long long)workspace_bytes,
                     (long long)lay.total);
@@ -142,9 +159,9 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
     float* ws = reinterpret_cast<float*>(workspace);
     char* scratch = reinterpret_cast<char*>(workspace) + lay.band_out_bytes;
     const int nb = (int)p->bands.size();
-    const int64_t prod_end = std::min(seg_end, n_total);      // nothing is produced past the end of the track
     const cudaStream_t caller = st;
-    const bool fork = p->multi_stream && nb > 1 && band_state == nullptr;
+    const bool fork = p->multi_stream && nb > 1 && band_state == nullptr && !direct;
+    bool first = true;
     bool used[UpmixPlan::N_AUX] = {false, false, false};
     int next_fused = 1;
     if (fork) CU_CHECK(cudaEventRecord(p->ev_fork, caller));
@@ -167,16 +184,28 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
         a.in_begin = in_begin;
         a.in_end = in_end;
         float* base = ws + (int64_t)bi * 3 * n_tracks * lay.ws_seg;
-        a.out_c = base;
-        a.out_l = base + (int64_t)n_tracks * lay.ws_seg;
-        a.out_r = base + 2 * (int64_t)n_tracks * lay.ws_seg;
-        a.out_stride = lay.ws_seg;
+        if (direct) {
+            a.out_c = out_c;
+            a.out_l = out_l;
+            a.out_r = out_r;
+            a.out_stride = out_stride;
+            a.accum = first ? 0 : 1;
+            a.mix = p->out_mode == UPMIX_OUT_FOLD && !p->fold_in_freq ? 1 : 0;
+            first = false;
+        } else {
+            a.out_c = base;
+            a.out_l = base + (int64_t)n_tracks * lay.ws_seg;
+            a.out_r = base + 2 * (int64_t)n_tracks * lay.ws_seg;
+            a.out_stride = lay.ws_seg;
+            a.accum = 0;
+            a.mix = 0;
+        }
         a.out_begin = seg_begin;
         a.seg_begin = std::max<int64_t>(seg_begin, 0);
         a.seg_end = prod_end;
         a.state = band_state ? band_state[bi] : nullptr;
         a.fold = p->fold_in_freq ? 1 : 0;
-        if (seg_begin < 0 || prod_end < seg_end) {
+        if (!direct && (seg_begin < 0 || prod_end < seg_end)) {
             // part of the requested range lies outside the track: those samples are zero
             CU_CHECK(cudaMemsetAsync(base, 0, (size_t)3 * n_tracks * lay.ws_seg * sizeof(float), st));
         }
@@ -227,8 +256,9 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
                 CU_CHECK(cudaStreamWaitEvent(caller, p->ev_join[si], 0));
             }
     }
-    CU_CHECK(launch_band_sum(ws, nb, n_tracks, seg_len, lay.ws_seg, out_c, out_l, out_r, out_stride,
-                             p->fold_in_freq ? 2 : p->out_mode, caller));
+    if (!direct)
+        CU_CHECK(launch_band_sum(ws, nb, n_tracks, seg_len, lay.ws_seg, out_c, out_l, out_r, out_stride,
+                                 p->fold_in_freq ? 2 : p->out_mode, caller));
     return UPMIX_OK;
 }
 
@@ -434,7 +464,8 @@ int upmix_plan_n_pipelines(const UpmixPlan* plan) { return plan ? (int)plan->ban
 int64_t upmix_workspace_bytes(const UpmixPlan* plan, int64_t seg_len, int n_tracks) {
     if (!plan) return fail(UPMIX_E_INVALID, "plan is NULL");
     if (seg_len < 0 || n_tracks < 1) return fail(UPMIX_E_INVALID, "bad seg_len / n_tracks");
-    return make_layout(plan, seg_len, n_tracks).total;
+    // enough for either way of summing the bands at this size (block streaming always stages)
+    return make_layout(plan, seg_len, n_tracks, !direct_sum(seg_len, n_tracks)).total;
 }
 
 int64_t upmix_segment_halo(const UpmixPlan* plan) { return plan ? plan->halo : fail(UPMIX_E_INVALID, "plan is NULL"); }
@@ -491,7 +522,7 @@ int upmix_stream_reset(const UpmixPlan* plan, void* state, int n_tracks, void* s
 int64_t upmix_stream_workspace_bytes(const UpmixPlan* plan, int n_new, int n_tracks) {
     if (!plan || n_new < 1 || n_tracks < 1) return fail(UPMIX_E_INVALID, "bad arguments");
     const int64_t stage = round_up(2LL * n_tracks * (plan->delay + n_new) * (int64_t)sizeof(float), 256);
-    return stage + make_layout(plan, n_new, n_tracks).total;
+    return stage + make_layout(plan, n_new, n_tracks, true).total;
 }
 
 int upmix_stream_block(const UpmixPlan* plan, void* state, int64_t samples_done, const float* in_l, const float* in_r,
@@ -551,7 +582,7 @@ int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, con
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (b.n_fft > FUSED_MAX_N) {
         // four-step path: the frame is slot 0 of a two-frame wave, its partner slot is zero
-        const Layout lay = make_layout(plan, b.hop, n_tracks);
+        const Layout lay = make_layout(plan, b.hop, n_tracks, false);
         if (workspace_bytes < lay.total) return fail(UPMIX_E_WORKSPACE, "workspace too small: %lld given, %lld needed", (long long)workspace_bytes, (long long)lay.total);
         if (plan->out_mode != UPMIX_OUT_LSCRS) return fail(UPMIX_E_UNSUPPORTED, "frame stepping on the four-step path needs Ls/C/Rs output");
         char* scratch = reinterpret_cast<char*>(workspace) + lay.band_out_bytes;
@@ -579,8 +610,9 @@ int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, con
     }
     float* rings[1] = {reinterpret_cast<float*>(ring)};
     const int64_t s0 = frame_index * b.hop;
+    // one band: its hop goes straight to the caller's outputs (no staging slot, no band sum)
     return run_segment(plan, blk_l, blk_r, s0, s0 + b.n_fft, INT64_MAX / 4, s0, s0 + b.hop, n_tracks, in_stride, out_c, out_l,
-                       out_r, out_stride, workspace, workspace_bytes, rings, st);
+                       out_r, out_stride, workspace, workspace_bytes, rings, st, true);
 }
 
 // ---- main.py's normalise + export on the device -------------------------------------------------

@@ -330,6 +330,34 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
         }
         __syncthreads();
 
+        // ---- where this frame's finished hop goes ---------------------------------------------------
+        // accum: the samples are added to what the output already holds (the bands before this one, in
+        // band order).  Those values are requested here, ahead of the inverse transforms, and wait in
+        // registers (ITE float4 per channel), so the copy-out does not stall on HBM.
+        const bool emit = f >= h0;
+        const int e_lo = (int)max(0LL, min((long long)H, a.seg_begin - s0));
+        const int e_hi = emit ? (int)max(0LL, min((long long)H, a.seg_end - s0)) : 0;
+        const bool accum = a.accum != 0;
+        const bool vec_out = e_lo == 0 && e_hi == H && (H % 4 == 0) && !a.mix &&
+                             (((reinterpret_cast<uintptr_t>(outp[1] + (s0 - a.out_begin)) | reinterpret_cast<uintptr_t>(outp[2] + (s0 - a.out_begin)) |
+                                (fold ? 0 : reinterpret_cast<uintptr_t>(outp[0] + (s0 - a.out_begin)))) & 15) == 0);   // CTA-uniform
+        constexpr int ITE = (N / 4 + 4 * T - 1) / (4 * T);       // float4 per thread and channel at hop = N/4
+        // (small sizes run 16 CTAs per SM on a 128-register budget: they load at the copy-out instead)
+        const bool pre = N >= 1024 && accum && vec_out && H <= 4 * T * ITE;
+        float4 prev[3][ITE];
+        if (pre) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                if (ch == 0 && fold) continue;
+                const float* __restrict__ po = outp[ch] + (s0 - a.out_begin);
+#pragma unroll
+                for (int it = 0; it < ITE; it++) {
+                    const int i = (tid + it * T) * 4;
+                    if (i < H) prev[ch][it] = __ldcs(reinterpret_cast<const float4*>(po + i));
+                }
+            }
+        }
+
         // ---- inverse transforms, synthesis window, overlap-add (oldest frame first) --------------
         auto ld_z = [&](int, int n, int, int) -> float2 { return Z[PAD<PF>(n)]; };
         auto st_lr = make_store([&](int, int n) -> float { return __ldg(syn + n); },
@@ -355,26 +383,56 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
         if (!TMA && f + 1 < h1) stage(f + 1);      // register variant: request the next frame before the copy-out
 
         // ---- emit the hop this frame finished, clear its ring slots --------------------------------
-        const bool emit = f >= h0;
-        const int e_lo = (int)max(0LL, min((long long)H, a.seg_begin - s0));
-        const int e_hi = emit ? (int)max(0LL, min((long long)H, a.seg_end - s0)) : 0;
-        const bool whole = e_lo == 0 && e_hi == H && (H % 4 == 0);
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            if (ch == 0 && fold) continue;                                  // no centre channel when folded
-            float* __restrict__ po = outp[ch] + (s0 - a.out_begin);
-            float* rg = ring + ch * N + base;
-            if (whole && (reinterpret_cast<uintptr_t>(po) & 15) == 0) {      // CTA-uniform: vector copy-out
-                for (int i = tid * 4; i < H; i += T * 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(rg + i);
-                    *reinterpret_cast<float4*>(rg + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    __stcs(reinterpret_cast<float4*>(po + i), v);
+        // mix: the fold-down epilogue Ls + 0.5 C / Rs + 0.5 C (bela/upmix.cpp:295-303).
+        if (a.mix) {
+            float* __restrict__ pl = outp[1] + (s0 - a.out_begin);
+            float* __restrict__ pr = outp[2] + (s0 - a.out_begin);
+            float* rc = ring + base;
+            float* rl = ring + N + base;
+            float* rr = ring + 2 * N + base;
+            for (int i = tid; i < H; i += T) {
+                const float hc = 0.5f * rc[i];
+                float vl = rl[i] + hc, vr = rr[i] + hc;
+                rc[i] = rl[i] = rr[i] = 0.f;
+                if (i >= e_lo && i < e_hi) {
+                    if (accum) { vl = pl[i] + vl; vr = pr[i] + vr; }
+                    pl[i] = vl;
+                    pr[i] = vr;
                 }
-            } else {
-                for (int i = tid; i < H; i += T) {
-                    const float v = rg[i];
-                    rg[i] = 0.f;
-                    if (i >= e_lo && i < e_hi) po[i] = v;
+            }
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                if (ch == 0 && fold) continue;                                  // no centre channel when folded
+                float* __restrict__ po = outp[ch] + (s0 - a.out_begin);
+                float* rg = ring + ch * N + base;
+                if (pre) {                                                       // previous sums already in registers
+#pragma unroll
+                    for (int it = 0; it < ITE; it++) {
+                        const int i = (tid + it * T) * 4;
+                        if (i < H) {
+                            const float4 v = *reinterpret_cast<const float4*>(rg + i);
+                            const float4 o = prev[ch][it];
+                            *reinterpret_cast<float4*>(rg + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            __stcs(reinterpret_cast<float4*>(po + i), make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w));
+                        }
+                    }
+                } else if (vec_out) {                                            // CTA-uniform: vector copy-out
+                    for (int i = tid * 4; i < H; i += T * 4) {
+                        float4 v = *reinterpret_cast<const float4*>(rg + i);
+                        *reinterpret_cast<float4*>(rg + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (accum) {
+                            const float4 o = __ldcs(reinterpret_cast<const float4*>(po + i));
+                            v = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
+                        }
+                        __stcs(reinterpret_cast<float4*>(po + i), v);
+                    }
+                } else {
+                    for (int i = tid; i < H; i += T) {
+                        const float v = rg[i];
+                        rg[i] = 0.f;
+                        if (i >= e_lo && i < e_hi) po[i] = accum ? po[i] + v : v;
+                    }
                 }
             }
         }
@@ -690,8 +748,16 @@ __global__ void __launch_bounds__(128, 4) col_inv_ola_kernel(const BandDev b, co
         for (int n1 = 0; n1 < COL_R / 4; n1++) {
             const long long s = s0 + n1 * N2;
             if (emit && s >= a.seg_begin && s < a.seg_end) {
+                const long long o = s - a.out_begin;
+                if (a.mix) {                     // fold-down epilogue: Ls + 0.5 C, Rs + 0.5 C
+                    const float hc = 0.5f * acc[0][n1];
+                    const float vl = acc[1][n1] + hc, vr = acc[2][n1] + hc;
+                    outp[1][o] = a.accum ? outp[1][o] + vl : vl;
+                    outp[2][o] = a.accum ? outp[2][o] + vr : vr;
+                } else {
 #pragma unroll
-                for (int ch = 0; ch < 3; ch++) outp[ch][s - a.out_begin] = acc[ch][n1];
+                    for (int ch = 0; ch < 3; ch++) outp[ch][o] = a.accum ? outp[ch][o] + acc[ch][n1] : acc[ch][n1];
+                }
             }
         }
 #pragma unroll

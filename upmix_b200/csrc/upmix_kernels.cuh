@@ -51,6 +51,10 @@ struct SegArgs {
     int fold;                       // fused kernel: fold the centre in the frequency domain -- emit
                                     // Ls + 0.5 C and Rs + 0.5 C in the Ls / Rs slots, no C transform
     float* state;                   // optional streaming state [track][3][n_fft]: ring carried between calls
+    int accum;                      // 0: finished samples are stored;  1: added to what out_* already holds
+                                    // (float32, band order = launch order: center_extraction.py:503-511)
+    int mix;                        // 0: out_c/out_l/out_r receive C, Ls, Rs;  1: fold-down epilogue --
+                                    // out_l receives Ls + 0.5 C, out_r Rs + 0.5 C, out_c is not touched
 };
 
 // Scratch of one wave of the large-N path.  Frames [frame0, frame0 + n_frames) of every track,
