@@ -1,3 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-UPMIX_DIRECT_MIN=1 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_parity.py::test_c_abi_argument_errors 2>&1 | tail -2
-python profiles/config_bench.py 2>&1 | tail -9
+for rep in 1 2; do
+for v in prev cur; do echo $v; if [ $v = cur ]; then unset UPMIX_B200_LIB; else export UPMIX_B200_LIB=$PWD/gpurun_variants/lib_$v.so; fi; python profiles/band_bench.py 3600 1024:d 8192:10 4096 512:d; done
+done

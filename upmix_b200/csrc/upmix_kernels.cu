@@ -32,6 +32,9 @@ namespace upmix {
 #ifndef UPMIX_REG_CAP
 #define UPMIX_REG_CAP 255
 #endif
+#ifndef UPMIX_MASK_CH
+#define UPMIX_MASK_CH 2           // mask rounds per chunk (2 bin quadruples = 4 masks in flight per thread)
+#endif
 #ifndef UPMIX_TMA_MIN_N
 #define UPMIX_TMA_MIN_N 2048      // frames of this size and larger are staged by TMA bulk copies
 #endif
@@ -59,7 +62,7 @@ UPMIX_FUSED_CFG_X(64, UPMIX_CFG_64)
 #endif
 UPMIX_FUSED_CFG_X(128, UPMIX_CFG_128)
 #ifndef UPMIX_CFG_256
-#define UPMIX_CFG_256 mkplan(8, 8, 4), mkplan(4, 4, 8), 32, 16
+#define UPMIX_CFG_256 mkplan(8, 8, 4), mkplan(4, 4, 8), 32, 12
 #endif
 UPMIX_FUSED_CFG_X(256, UPMIX_CFG_256)
 #ifndef UPMIX_CFG_512
@@ -232,108 +235,12 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
         const long long s0 = f * H;
         const int base = (int)(f % K) * H;
 
-        // ---- forward: Z = FFT_N( ana * (L + iR) ) -----------------------------------------------
-        if (TMA && in_by_tma) {
-            mbar_wait(&in_bar, in_phase);
-            in_phase ^= 1;
-        }
-        auto ld_in = [&](int, int n, int it, int r) -> float2 {
-            const float wn = xw[it][r];
-            if constexpr (TMA) return make_float2(SL[n] * wn, SR[n] * wn);
-            else return make_float2(xin[it][r].x * wn, xin[it][r].y * wn);
-        };
-        auto st_z = make_store([&](int, int k, float2 v, NoAux) { Z[PAD<PF>(k)] = v; });
-        fft_smem<PF, -1, T, 1, TMA>(Z, tid, tw, ld_in, st_z);      // TMA: in place, SL/SR live inside Z
-
-        // ---- split / gain / mask; Y1 = Ls + i*Rs in place, C packed for the half-size inverse ---
-        // A thread takes bins k and M-k (and their mirrors N-k, M+k) per item, CH items per chunk.  A
-        // chunk whose gains are all zero only stores zeros (most of a low band's spectrum); otherwise the
-        // CH*2 masks are straight-line code, so their MUFU / dependency latencies overlap.
-        {
-            constexpr int ITM = (M / 2 + 1 + T - 1) / T;
-            constexpr int CH = 3;                        // iterations whose table loads fly together
-#pragma unroll 1
-            for (int it0 = 0; it0 < ITM; it0 += CH) {
-                float g1[CH], g2[CH];
-                float2 wp[CH];
-                bool any = false;
-#pragma unroll
-                for (int i = 0; i < CH; i++) {
-                    const int k = min(tid + (it0 + i) * T, M / 2);
-                    g1[i] = __ldg(gain + k);
-                    g2[i] = __ldg(gain + M - k);
-                    wp[i] = __ldg(twp + k);
-                    any = any || g1[i] != 0.f || g2[i] != 0.f;   // merged tables: non-zero gains come first
-                }
-                if (!any) {
-                    const float2 zero = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int i = 0; i < CH; i++) {
-                        const int k = tid + (it0 + i) * T;
-                        if (k <= M / 2) {
-                            Z[PAD<PF>(k)] = zero;
-                            Z[PAD<PF>((N - k) & (N - 1))] = zero;
-                            Z[PAD<PF>(M - k)] = zero;
-                            Z[PAD<PF>(M + k)] = zero;
-                            if (!fold) {
-                                Cz[PAD<PH>(k)] = zero;
-                                if (k > 0) Cz[PAD<PH>(M - k)] = zero;
-                            }
-                        }
-                    }
-                    continue;
-                }
-#pragma unroll
-                for (int i = 0; i < CH; i++) {
-                    const int kq = tid + (it0 + i) * T;
-                    const bool live = kq <= M / 2;
-                    const int k = min(kq, M / 2);        // surplus threads recompute bin M/2 and store nothing
-                    const int k2 = M - k;
-                    const int km = (N - k) & (N - 1);
-                    const float2 a1 = Z[PAD<PF>(k)], b1 = Z[PAD<PF>(km)];
-                    const float2 a2 = Z[PAD<PF>(k2)], b2 = Z[PAD<PF>(M + k)];
-                    float2 c1, y1, y1m, c2, y2, y2m;
-                    if constexpr (MODE == MODE_MERGED) {
-                        mask_bin_merged(a1, b1, g1[i], gain + k, b.n_gains, b.gain_stride, y1, y1m, c1);
-                        mask_bin_merged(a2, b2, g2[i], gain + k2, b.n_gains, b.gain_stride, y2, y2m, c2);
-                    } else {
-                        mask_bin(a1, b1, g1[i], y1, y1m, c1);
-                        mask_bin(a2, b2, g2[i], y2, y2m, c2);
-                    }
-                    if (fold) {
-                        // (Ls + C/2) + i (Rs + C/2) = (Ls + i Rs) + (1+i) C/2: the fold-down is linear, so
-                        // it is taken here and the centre needs no transform of its own
-                        y1 = make_float2(y1.x + 0.5f * (c1.x - c1.y), y1.y + 0.5f * (c1.x + c1.y));
-                        y1m = make_float2(y1m.x + 0.5f * (c1.x + c1.y), y1m.y + 0.5f * (c1.x - c1.y));
-                        y2 = make_float2(y2.x + 0.5f * (c2.x - c2.y), y2.y + 0.5f * (c2.x + c2.y));
-                        y2m = make_float2(y2m.x + 0.5f * (c2.x + c2.y), y2m.y + 0.5f * (c2.x - c2.y));
-                    }
-                    if (live) {
-                        Z[PAD<PF>(k)] = y1;
-                        Z[PAD<PF>(km)] = y1m;
-                        Z[PAD<PF>(k2)] = y2;
-                        Z[PAD<PF>(M + k)] = y2m;
-                    }
-                    if (!fold) {
-                        // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);
-                        // IFFT_M(z)[m] = c[2m] + i c[2m+1]
-                        const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
-                        const float2 B = make_float2(c1.x - c2.x, c1.y + c2.y);
-                        const float2 D = cmul(B, make_float2(wp[i].x, -wp[i].y));
-                        if (live) {
-                            Cz[PAD<PH>(k)] = make_float2(A.x - D.y, A.y + D.x);
-                            if (k > 0) Cz[PAD<PH>(M - k)] = make_float2(A.x + D.y, D.x - A.y);
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-
         // ---- where this frame's finished hop goes ---------------------------------------------------
         // accum: the samples are added to what the output already holds (the bands before this one, in
-        // band order).  Those values are requested here, ahead of the inverse transforms, and wait in
-        // registers (ITE float4 per channel), so the copy-out does not stall on HBM.
+        // band order).  Those values are requested here, at the top of the frame, and wait in
+        // registers (ITE float4 per channel) through the whole frame, so the copy-out does not stall on HBM
+        // (requested after the Ls + iRs inverse they were still in flight at the copy-out: 6 % of the
+        // 1024-point kernel's stall samples sat on that one addition).
         const bool emit = f >= h0;
         const int e_lo = (int)max(0LL, min((long long)H, a.seg_begin - s0));
         const int e_hi = emit ? (int)max(0LL, min((long long)H, a.seg_end - s0)) : 0;
@@ -357,6 +264,118 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
                 }
             }
         }
+
+        // ---- forward: Z = FFT_N( ana * (L + iR) ) -----------------------------------------------
+        if (TMA && in_by_tma) {
+            mbar_wait(&in_bar, in_phase);
+            in_phase ^= 1;
+        }
+        auto ld_in = [&](int, int n, int it, int r) -> float2 {
+            const float wn = xw[it][r];
+            if constexpr (TMA) return make_float2(SL[n] * wn, SR[n] * wn);
+            else return make_float2(xin[it][r].x * wn, xin[it][r].y * wn);
+        };
+        auto st_z = make_store([&](int, int k, float2 v, NoAux) { Z[PAD<PF>(k)] = v; });
+        fft_smem<PF, -1, T, 1, TMA>(Z, tid, tw, ld_in, st_z);      // TMA: in place, SL/SR live inside Z
+
+        // ---- split / gain / mask; Y1 = Ls + i*Rs in place, C packed for the half-size inverse ---
+        // An item is the bin quadruple k, M-k and their mirrors N-k, M+k, for k = 0 .. M/2.  Items
+        // 0 .. M/2-1 go in rounds of T threads, CH rounds per chunk; the last one (k = M/2, a single bin
+        // pair) is one thread's epilogue, so no round runs for it alone.  A chunk whose gains are all
+        // zero only stores zeros (most of a low band's spectrum); otherwise its CH*2 masks are
+        // straight-line code, so their MUFU / dependency latencies overlap.
+        {
+            constexpr int HALF = M / 2;
+            constexpr int ROUNDS = (HALF + T - 1) / T;
+            // measured (same run, ms per band-hour): 2 rounds per chunk 1024 5.64 -> 5.39, 512 5.49 -> 5.32 (4 spill
+            // there); 4 per chunk for the 32-points-per-thread sizes: 8192 7.08 -> 7.03, 4096 6.25 -> 6.20
+            constexpr int WANT = N >= 2048 ? 2 * UPMIX_MASK_CH : UPMIX_MASK_CH;
+            constexpr int CH = ROUNDS % WANT == 0 ? WANT : (ROUNDS % 2 == 0 ? 2 : 1);
+            auto zero_item = [&](int k) {
+                const float2 zero = make_float2(0.f, 0.f);
+                Z[PAD<PF>(k)] = zero;
+                Z[PAD<PF>((N - k) & (N - 1))] = zero;
+                Z[PAD<PF>(M - k)] = zero;
+                Z[PAD<PF>(M + k)] = zero;
+                if (!fold) {
+                    Cz[PAD<PH>(k)] = zero;
+                    if (k > 0) Cz[PAD<PH>(M - k)] = zero;
+                }
+            };
+            auto mask_item = [&](int k, bool live, float g1, float g2, float2 wp) {
+                const int k2 = M - k;
+                const int km = (N - k) & (N - 1);
+                const float2 a1 = Z[PAD<PF>(k)], b1 = Z[PAD<PF>(km)];
+                const float2 a2 = Z[PAD<PF>(k2)], b2 = Z[PAD<PF>(M + k)];
+                float2 c1, y1, y1m, c2, y2, y2m;
+                if constexpr (MODE == MODE_MERGED) {
+                    mask_bin_merged(a1, b1, g1, gain + k, b.n_gains, b.gain_stride, y1, y1m, c1);
+                    mask_bin_merged(a2, b2, g2, gain + k2, b.n_gains, b.gain_stride, y2, y2m, c2);
+                } else {
+                    mask_bin(a1, b1, g1, y1, y1m, c1);
+                    mask_bin(a2, b2, g2, y2, y2m, c2);
+                }
+                if (fold) {
+                    // (Ls + C/2) + i (Rs + C/2) = (Ls + i Rs) + (1+i) C/2: the fold-down is linear, so
+                    // it is taken here and the centre needs no transform of its own
+                    y1 = make_float2(y1.x + 0.5f * (c1.x - c1.y), y1.y + 0.5f * (c1.x + c1.y));
+                    y1m = make_float2(y1m.x + 0.5f * (c1.x + c1.y), y1m.y + 0.5f * (c1.x - c1.y));
+                    y2 = make_float2(y2.x + 0.5f * (c2.x - c2.y), y2.y + 0.5f * (c2.x + c2.y));
+                    y2m = make_float2(y2m.x + 0.5f * (c2.x + c2.y), y2m.y + 0.5f * (c2.x - c2.y));
+                }
+                if (live) {
+                    Z[PAD<PF>(k)] = y1;
+                    Z[PAD<PF>(km)] = y1m;
+                    Z[PAD<PF>(k2)] = y2;
+                    Z[PAD<PF>(M + k)] = y2m;
+                }
+                if (!fold) {
+                    // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);
+                    // IFFT_M(z)[m] = c[2m] + i c[2m+1]
+                    const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
+                    const float2 B = make_float2(c1.x - c2.x, c1.y + c2.y);
+                    const float2 D = cmul(B, make_float2(wp.x, -wp.y));
+                    if (live) {
+                        Cz[PAD<PH>(k)] = make_float2(A.x - D.y, A.y + D.x);
+                        if (k > 0) Cz[PAD<PH>(M - k)] = make_float2(A.x + D.y, D.x - A.y);
+                    }
+                }
+            };
+#pragma unroll 1
+            for (int it0 = 0; it0 < ROUNDS; it0 += CH) {
+                float g1[CH], g2[CH];
+                float2 wp[CH];
+                bool any = false;
+#pragma unroll
+                for (int i = 0; i < CH; i++) {
+                    const int k = min(tid + (it0 + i) * T, HALF - 1);
+                    g1[i] = __ldg(gain + k);
+                    g2[i] = __ldg(gain + M - k);
+                    wp[i] = __ldg(twp + k);
+                    any = any || g1[i] != 0.f || g2[i] != 0.f;   // merged tables: non-zero gains come first
+                }
+                if (!any) {
+#pragma unroll
+                    for (int i = 0; i < CH; i++) {
+                        const int k = tid + (it0 + i) * T;
+                        if (HALF % T == 0 || k < HALF) zero_item(k);
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int i = 0; i < CH; i++) {
+                    const int kq = tid + (it0 + i) * T;
+                    // surplus threads (HALF not a multiple of T) recompute the last item and store nothing
+                    mask_item(min(kq, HALF - 1), HALF % T == 0 || kq < HALF, g1[i], g2[i], wp[i]);
+                }
+            }
+            if (tid == T - 1) {                          // k = M/2: bins M/2 and N - M/2, taken twice by the item code
+                const float g = __ldg(gain + HALF);
+                if (g == 0.f) zero_item(HALF);
+                else mask_item(HALF, true, g, g, __ldg(twp + HALF));
+            }
+        }
+        __syncthreads();
 
         // ---- inverse transforms, synthesis window, overlap-add (oldest frame first) --------------
         auto ld_z = [&](int, int n, int, int) -> float2 { return Z[PAD<PF>(n)]; };
