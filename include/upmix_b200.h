@@ -148,6 +148,15 @@ int upmix_pcm16_to_planar(const int16_t* interleaved, int64_t n, float* l, float
                           int64_t workspace_bytes, void* stream);
 int upmix_stereo_to_pcm16(const float* interleaved, int64_t n, int16_t* out, void* stream);
 
+/* Causal FIR filter, the arithmetic of apply_fir_filter (python-prototype/filter_design.py:54-59:
+ * scipy.signal.lfilter(taps, 1.0, wave)): y[i] = sum_k taps[k] x[i-k], x[i<0] = 0, n outputs per track.
+ * x, y, taps: device float32; track t at x + t*x_stride / y + t*y_stride; 1 <= n_taps <= 16384; y must
+ * not overlap x.  The taps themselves (design_lr4_hp_fir / design_lr4_lp_fir, filter_design.py:25-52)
+ * are designed on the host.  Nothing on the centre-extraction path calls this (the prototype does not
+ * either: filter_design is imported by no other file). */
+int upmix_fir_filter(const float* x, int64_t n, int n_tracks, int64_t x_stride, const float* taps, int n_taps, float* y,
+                     int64_t y_stride, void* stream);
+
 /* Measurement helpers (bench.py): number of kernels this library launched since the last reset, and
  * the FP32 FMA throughput of the device (the roofline denominator of this FP32-bound path). */
 int64_t upmix_debug_launch_count(int reset);

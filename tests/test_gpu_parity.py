@@ -546,3 +546,28 @@ def test_direct_band_sum_is_identical_to_staged(ce, monkeypatch):
                 res[mode] = whole + batch
             for x, y in zip(res["staged"], res["direct"]):
                 assert torch.equal(x, y), (edges, fold)
+
+
+def test_fir_filter_vs_reference_fixture(ce, golden_dir):
+    """apply_fir_filter (filter_design.py:54-59, scipy.signal.lfilter in float64) on the device in float32:
+    >= 100 dB SNR against the reference's own outputs; shapes, dtypes and the pass-through taps."""
+    import torch
+    from upmix_b200 import filter_design as fd
+    g = _load(golden_dir, "fir.npz")
+    L, R = g["in_L"], g["in_R"]
+    for x, taps, ref in ((L.astype(np.float64), g["ref_hp"], g["ref_y_hp"]), (R.astype(np.float64), g["ref_lp"], g["ref_y_lp"]),
+                         (L, g["ref_hp_short"], g["ref_y_short"])):
+        y = fd.apply_fir_filter(x, taps)
+        assert y.shape == ref.shape and y.dtype == ref.dtype
+        snr = uo.snr_db(ref, y)
+        err = float(np.max(np.abs(ref - y)))
+        assert snr >= 100.0 and err <= 1e-5, (snr, err)
+    assert np.array_equal(fd.apply_fir_filter(L, g["ref_pass"]), L)
+    # tracks along the first axis, ragged lengths around the tile size, CUDA tensors in and out
+    for n in (1, 7, 2047, 2048, 2049, 5000):
+        x = np.stack([L[:n], R[:n]])
+        y = fd.apply_fir_filter(torch.from_numpy(x).cuda(), g["ref_hp_short"])
+        assert y.is_cuda and y.dtype == torch.float32 and tuple(y.shape) == (2, n)
+        from scipy.signal import lfilter
+        ref = lfilter(g["ref_hp_short"].astype(np.float64), 1.0, x.astype(np.float64))
+        assert float(np.max(np.abs(ref - y.cpu().numpy()))) <= 1e-6

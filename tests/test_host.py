@@ -132,3 +132,20 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_fir_design_matches_reference_fixture(golden_dir):
+    """design_lr4_hp_fir / design_lr4_lp_fir (filter_design.py:25-52) are host code: bit-identical taps
+    when scipy is the version the fixture was made with, equal to float32 rounding otherwise."""
+    import scipy
+    from upmix_b200 import filter_design as fd
+    g = np.load(os.path.join(golden_dir, "fir.npz"))
+    got = {"ref_hp": fd.design_lr4_hp_fir(48000, 180.0, 1025), "ref_lp": fd.design_lr4_lp_fir(48000, 180.0, 1025),
+           "ref_hp_short": fd.design_lr4_hp_fir(44100, 2000.0, 129), "ref_pass": fd.design_lr4_lp_fir(48000, 0.0)}
+    for k, v in got.items():
+        assert v.dtype == np.float32 and v.shape == g[k].shape
+        if scipy.__version__ == str(g["scipy_version"]):
+            assert np.array_equal(v, g[k]), k
+        else:
+            assert np.allclose(v, g[k], rtol=0, atol=1e-7), k
+    assert np.array_equal(fd.design_lr4_hp_fir(48000, -1.0), np.array([1.0], dtype=np.float32))

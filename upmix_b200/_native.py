@@ -74,6 +74,7 @@ def load_library():
     _sig(lib.upmix_export_mix, i32, [i32, ctypes.c_float, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp])
     _sig(lib.upmix_pcm16_to_planar, i32, [vp, i64, vp, vp, vp, vp, i64, vp])
     _sig(lib.upmix_stereo_to_pcm16, i32, [vp, i64, vp, vp])
+    _sig(lib.upmix_fir_filter, i32, [vp, i64, i32, i64, vp, i32, vp, i64, vp])
     _sig(lib.upmix_debug_launch_count, i64, [i32])
     _sig(lib.upmix_measure_fp32_tflops, i32, [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)])
     _lib = lib
@@ -86,9 +87,23 @@ EXPORTS = ("upmix_last_error", "upmix_version", "upmix_plan_create", "upmix_plan
            "upmix_stream_delay", "upmix_stream_reset", "upmix_stream_block", "upmix_process_host",
            "upmix_frame_step", "upmix_debug_launch_count", "upmix_measure_fp32_tflops",
            "upmix_peak_workspace_bytes", "upmix_peak3", "upmix_export_mix", "upmix_pcm16_to_planar",
-           "upmix_stereo_to_pcm16")
+           "upmix_stereo_to_pcm16", "upmix_fir_filter")
 
 EXPORT_MODES = {"AB": 0, "split": 1, "stereo_sum": 2}
+
+
+def fir_filter(x, taps):
+    """y[..., i] = sum_k taps[k] x[..., i-k] (causal, zero history) for a float32 CUDA tensor x [n] or
+    [tracks, n] and float32 CUDA taps [n_taps] (upmix_fir_filter)."""
+    torch = _torch()
+    lib = load_library()
+    x2 = x.reshape(-1, x.shape[-1]).contiguous()
+    y = torch.empty_like(x2)
+    taps = taps.contiguous()
+    with torch.cuda.device(x.device):
+        _check(lib.upmix_fir_filter(x2.data_ptr(), x2.shape[1], x2.shape[0], x2.shape[1], taps.data_ptr(), taps.numel(),
+                                    y.data_ptr(), x2.shape[1], torch.cuda.current_stream(x.device).cuda_stream))
+    return y.reshape(x.shape)
 
 
 def peak3(c, l, r):

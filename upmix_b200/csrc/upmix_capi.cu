@@ -657,6 +657,15 @@ int upmix_stereo_to_pcm16(const float* interleaved, int64_t n, int16_t* out, voi
     return UPMIX_OK;
 }
 
+int upmix_fir_filter(const float* x, int64_t n, int n_tracks, int64_t x_stride, const float* taps, int n_taps, float* y,
+                     int64_t y_stride, void* stream) {
+    if (!x || !taps || !y) return fail(UPMIX_E_INVALID, "NULL pointer");
+    if (n < 0 || n_tracks < 1 || n_tracks > 65535) return fail(UPMIX_E_INVALID, "bad length / n_tracks");
+    if (n_taps < 1 || n_taps > 16384) return fail(UPMIX_E_UNSUPPORTED, "n_taps must be in [1, 16384], got %d", n_taps);
+    CU_CHECK(launch_fir(x, n, n_tracks, x_stride, taps, n_taps, y, y_stride, reinterpret_cast<cudaStream_t>(stream)));
+    return UPMIX_OK;
+}
+
 int64_t upmix_debug_launch_count(int reset) { return (int64_t)launch_count(reset != 0); }
 
 int upmix_measure_fp32_tflops(int device, double* tflops, int* sm_count) {

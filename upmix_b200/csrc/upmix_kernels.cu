@@ -1076,6 +1076,69 @@ cudaError_t launch_export_mix(const float* c, const float* l, const float* r, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// Causal FIR filter (filter_design.py:54-59: scipy.signal.lfilter(taps, 1.0, wave)):
+//   y[i] = sum_k taps[k] * x[i - k],  x[i < 0] = 0,  same length as x.
+// A CTA produces FIR_TILE consecutive outputs of one track: the input span and the reversed taps sit in
+// shared memory; a thread owns 8 consecutive outputs and slides a 16-sample register window over the
+// span, 8 taps per step (two 128-bit loads of samples, two broadcast 128-bit loads of taps, 64 FMAs).
+// ---------------------------------------------------------------------------------------------
+constexpr int FIR_THREADS = 256, FIR_PER_THREAD = 8, FIR_TILE = FIR_THREADS * FIR_PER_THREAD;
+__global__ void __launch_bounds__(FIR_THREADS) fir_kernel(const float* __restrict__ x, long long n, long long x_stride,
+                                                          const float* __restrict__ taps, int n_taps, int kpad,
+                                                          float* __restrict__ y, long long y_stride) {
+    extern __shared__ __align__(16) float fir_smem[];
+    float* hr = fir_smem;                 // [kpad]  hr[m] = taps[n_taps-1-m], zero beyond n_taps
+    float* xs = fir_smem + kpad;          // [FIR_TILE + kpad + 8]  xs[t] = x[i0 - (n_taps-1) + t]
+    const int tid = threadIdx.x;
+    const long long i0 = (long long)blockIdx.x * FIR_TILE;
+    const float* __restrict__ xt = x + (long long)blockIdx.y * x_stride;
+    float* __restrict__ yt = y + (long long)blockIdx.y * y_stride;
+    for (int m = tid; m < kpad; m += FIR_THREADS) hr[m] = m < n_taps ? __ldg(taps + (n_taps - 1 - m)) : 0.f;
+    const int span = FIR_TILE + kpad + 8;
+    for (int t = tid; t < span; t += FIR_THREADS) {
+        const long long i = i0 - (n_taps - 1) + t;
+        xs[t] = (i >= 0 && i < n) ? __ldg(xt + i) : 0.f;
+    }
+    __syncthreads();
+    const int o = tid * FIR_PER_THREAD;
+    float acc[FIR_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < FIR_PER_THREAD; j++) acc[j] = 0.f;
+    float w[16];
+    *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(xs + o);
+    *reinterpret_cast<float4*>(w + 4) = *reinterpret_cast<const float4*>(xs + o + 4);
+#pragma unroll 2
+    for (int m0 = 0; m0 < kpad; m0 += 8) {
+        *reinterpret_cast<float4*>(w + 8) = *reinterpret_cast<const float4*>(xs + o + m0 + 8);
+        *reinterpret_cast<float4*>(w + 12) = *reinterpret_cast<const float4*>(xs + o + m0 + 12);
+        float h[8];
+        *reinterpret_cast<float4*>(h) = *reinterpret_cast<const float4*>(hr + m0);
+        *reinterpret_cast<float4*>(h + 4) = *reinterpret_cast<const float4*>(hr + m0 + 4);
+#pragma unroll
+        for (int mm = 0; mm < 8; mm++)
+#pragma unroll
+            for (int j = 0; j < FIR_PER_THREAD; j++) acc[j] = fmaf(h[mm], w[j + mm], acc[j]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) w[j] = w[j + 8];
+    }
+#pragma unroll
+    for (int j = 0; j < FIR_PER_THREAD; j++)
+        if (i0 + o + j < n) yt[i0 + o + j] = acc[j];
+}
+
+cudaError_t launch_fir(const float* x, long long n, int n_tracks, long long x_stride, const float* taps, int n_taps, float* y,
+                       long long y_stride, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const int kpad = (n_taps + 7) / 8 * 8;
+    const int smem = (kpad + FIR_TILE + kpad + 8) * (int)sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    fir_kernel<<<dim3((unsigned)((n + FIR_TILE - 1) / FIR_TILE), n_tracks), FIR_THREADS, smem, st>>>(x, n, x_stride, taps, n_taps, kpad, y,
+                                                                                                      y_stride);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP32 peak probe: 8 independent FMA chains per thread, enough warps to fill every SM.  Used by
 // bench.py for the roofline denominator (MEASURED_PEAKS.json has no FP32 figure).
 // ---------------------------------------------------------------------------------------------

@@ -27,6 +27,8 @@ cudaError_t launch_peak3(const float* c, const float* l, const float* r, long lo
                          float* out3, cudaStream_t st);
 cudaError_t launch_export_mix(const float* c, const float* l, const float* r, const float* in_l, const float* in_r,
                               long long n, float scale, int mode, float* out_a, float* out_b, float* out_c, cudaStream_t st);
+cudaError_t launch_fir(const float* x, long long n, int n_tracks, long long x_stride, const float* taps, int n_taps, float* y,
+                       long long y_stride, cudaStream_t st);
 cudaError_t launch_fma_peak(float* out, int blocks, int iters, cudaStream_t st);
 unsigned long long launch_count(bool reset);
 
