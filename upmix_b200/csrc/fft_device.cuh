@@ -20,8 +20,15 @@
 
 namespace upmix {
 
-// Complex add / subtract as ONE packed instruction (sm_100 add.f32x2, SASS FADD2): the butterflies are
-// add-heavy, and halving their instruction count frees issue slots (the FMA pipe itself is not the limit).
+// Packed FP32x2 arithmetic (sm_100: add/mul/fma.f32x2, SASS FADD2 / FMUL2 / FFMA2).  The packed forms take
+// operand modifiers -- swapped halves (.LO_HI), one-half negation (.NP), a scalar or an immediate broadcast
+// to both halves (.F32) -- so with a complex number in a register pair
+//   * complex add / subtract is ONE instruction,
+//   * multiplication by +-i is free (it folds into the consuming add as swap + half negation),
+//   * a complex multiply is TWO:  t = (a.y, a.x) * (-b.y, b.y);  r = a * (b.x, b.x) + t,
+// against 2 / 4 scalar instructions.  The butterflies and the mask are issue-bound (the FMA pipe itself
+// is not the limit), so halving their instruction count is what counts.  nvcc maps the intrinsics below
+// onto those modifiers (checked in the SASS: FMUL2 R, -R.F32x2.LO_HI.NP, R.F32 ; FFMA2 R, R.F32x2.HI_LO, R.F32, R).
 #ifndef UPMIX_SCALAR_CADD
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
@@ -29,9 +36,21 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 #endif
+#ifndef UPMIX_SCALAR_CMUL
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    const float2 t = __fmul2_rn(make_float2(a.y, a.x), make_float2(-b.y, b.y));
+    return __ffma2_rn(a, make_float2(b.x, b.x), t);
+}
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+// a * s + b with a real scalar s
+__device__ __forceinline__ float2 caxpy(float2 a, float s, float2 b) { return __ffma2_rn(a, make_float2(s, s), b); }
+#else
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float2 caxpy(float2 a, float s, float2 b) { return make_float2(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y)); }
+#endif
 
 // multiply by DIR*i  (DIR = -1: forward transform, e^{-i...};  DIR = +1: inverse)
 template <int DIR>
@@ -49,8 +68,9 @@ __device__ __forceinline__ float2 mul_w32(float2 z, int m) {
                             0.55557023301960222f, 0.38268343236508977f, 0.19509032201612827f, 0.f};
     if (m == 0) return z;
     if (m == 8) return mul_i<DIR>(z);
-    if (m == 4) return make_float2(H * (z.x - s * z.y), H * (z.y + s * z.x));
-    if (m == 12) return make_float2(H * (-z.x - s * z.y), H * (s * z.x - z.y));
+    // (1 + s i)/sqrt2 and (-1 + s i)/sqrt2: one packed add (z +- i z) and one packed scale
+    if (m == 4) return cscale(cadd(z, make_float2(-s * z.y, s * z.x)), H);
+    if (m == 12) return cscale(cadd(z, make_float2(s * z.y, -s * z.x)), -H);
     // general: cos(2 pi m/32) = C[m] (m<8) or -C[16-m]; sin(2 pi m/32) = C[8-m] (m<8) or C[m-8]
     const float c = m < 8 ? C[m] : -C[16 - m];
     const float sn = m < 8 ? C[8 - m] : C[m - 8];
@@ -505,17 +525,19 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // far from the approximate divider's limits.
 __device__ __forceinline__ void mask_bin(float2 a, float2 b, float g, float2& y_lo, float2& y_hi, float2& c) {
     constexpr float EPS = 1e-12f;
-    const float px = a.x + b.x, py = a.y - b.y, qx = a.x - b.x, qy = a.y + b.y;
+    const float2 P = cadd(a, make_float2(b.x, -b.y));          // a + conj b
+    const float2 Q = cadd(a, make_float2(-b.x, b.y));          // a - conj b
     const float hg = 0.5f * g;
-    const float ml = hg * sqrt_approx(px * px + py * py);
-    const float mr = hg * sqrt_approx(qx * qx + qy * qy);
+    const float ml = hg * sqrt_approx(fmaf(P.x, P.x, P.y * P.y));
+    const float mr = hg * sqrt_approx(fmaf(Q.x, Q.x, Q.y * Q.y));
     const float m = ml * mr;
     const float sden = ml + mr + EPS;
     const float cf = (m * (sden - fabsf(ml - mr))) * rcp_approx((m + EPS) * sden);
     const float t = (0.5f * cf) * hg;
-    c = make_float2(t * (px + qy), t * (py - qx));
-    y_lo = make_float2(g * a.x - c.x + c.y, g * a.y - c.x - c.y);
-    y_hi = make_float2(g * b.x - c.x - c.y, g * b.y - c.x + c.y);
+    c = cscale(cadd(P, make_float2(Q.y, -Q.x)), t);            // t (P - i Q) = t (px + qy, py - qx)
+    const float2 u = cadd(make_float2(c.x, c.x), make_float2(-c.y, c.y));   // (1+i) C = (cx - cy, cx + cy)
+    y_lo = caxpy(a, g, make_float2(-u.x, -u.y));
+    y_hi = caxpy(b, g, make_float2(-u.y, -u.x));               // (1+i) conj C = (cx + cy, cx - cy)
 }
 
 // Bands that share an STFT (same size, hop and windows) share the forward transform and -- the inverse

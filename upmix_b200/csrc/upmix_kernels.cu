@@ -272,8 +272,8 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
         }
         auto ld_in = [&](int, int n, int it, int r) -> float2 {
             const float wn = xw[it][r];
-            if constexpr (TMA) return make_float2(SL[n] * wn, SR[n] * wn);
-            else return make_float2(xin[it][r].x * wn, xin[it][r].y * wn);
+            if constexpr (TMA) return cscale(make_float2(SL[n], SR[n]), wn);
+            else return cscale(xin[it][r], wn);
         };
         auto st_z = make_store([&](int, int k, float2 v, NoAux) { Z[PAD<PF>(k)] = v; });
         fft_smem<PF, -1, T, 1, TMA>(Z, tid, tw, ld_in, st_z);      // TMA: in place, SL/SR live inside Z
@@ -318,10 +318,12 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
                 if (fold) {
                     // (Ls + C/2) + i (Rs + C/2) = (Ls + i Rs) + (1+i) C/2: the fold-down is linear, so
                     // it is taken here and the centre needs no transform of its own
-                    y1 = make_float2(y1.x + 0.5f * (c1.x - c1.y), y1.y + 0.5f * (c1.x + c1.y));
-                    y1m = make_float2(y1m.x + 0.5f * (c1.x + c1.y), y1m.y + 0.5f * (c1.x - c1.y));
-                    y2 = make_float2(y2.x + 0.5f * (c2.x - c2.y), y2.y + 0.5f * (c2.x + c2.y));
-                    y2m = make_float2(y2m.x + 0.5f * (c2.x + c2.y), y2m.y + 0.5f * (c2.x - c2.y));
+                    const float2 u1 = cadd(make_float2(c1.x, c1.x), make_float2(-c1.y, c1.y));   // (1+i) C
+                    const float2 u2 = cadd(make_float2(c2.x, c2.x), make_float2(-c2.y, c2.y));
+                    y1 = caxpy(u1, 0.5f, y1);
+                    y1m = caxpy(make_float2(u1.y, u1.x), 0.5f, y1m);
+                    y2 = caxpy(u2, 0.5f, y2);
+                    y2m = caxpy(make_float2(u2.y, u2.x), 0.5f, y2m);
                 }
                 if (live) {
                     Z[PAD<PF>(k)] = y1;
@@ -332,12 +334,12 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
                 if (!fold) {
                     // z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]);
                     // IFFT_M(z)[m] = c[2m] + i c[2m+1]
-                    const float2 A = make_float2(c1.x + c2.x, c1.y - c2.y);
-                    const float2 B = make_float2(c1.x - c2.x, c1.y + c2.y);
+                    const float2 A = cadd(c1, make_float2(c2.x, -c2.y));
+                    const float2 B = cadd(c1, make_float2(-c2.x, c2.y));
                     const float2 D = cmul(B, make_float2(wp.x, -wp.y));
                     if (live) {
-                        Cz[PAD<PH>(k)] = make_float2(A.x - D.y, A.y + D.x);
-                        if (k > 0) Cz[PAD<PH>(M - k)] = make_float2(A.x + D.y, D.x - A.y);
+                        Cz[PAD<PH>(k)] = cadd(A, make_float2(-D.y, D.x));
+                        if (k > 0) Cz[PAD<PH>(M - k)] = cadd(make_float2(A.x, -A.y), make_float2(D.y, D.x));
                     }
                 }
             };
@@ -382,8 +384,9 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
         auto st_lr = make_store([&](int, int n) -> float { return __ldg(syn + n); },
                                 [&](int, int n, float2 v, float wn) {
                                     const int p = (base + n) & (N - 1);
-                                    ring[N + p] += v.x * wn;
-                                    ring[2 * N + p] += v.y * wn;
+                                    const float2 acc = caxpy(v, wn, make_float2(ring[N + p], ring[2 * N + p]));
+                                    ring[N + p] = acc.x;
+                                    ring[2 * N + p] = acc.y;
                                 });
         fft_smem<PF, +1, T, 1, true>(Z, tid, tw, ld_z, st_lr);
         if (TMA && f + 1 < h1) stage(f + 1);       // Z is idle from here to the next frame's first pass
@@ -392,10 +395,7 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
                                [&](int, int m, float2 v, float2 wn) {
                                    const int p = (base + 2 * m) & (N - 1);
                                    float2* q = reinterpret_cast<float2*>(ring + p);
-                                   float2 acc = *q;
-                                   acc.x += v.x * wn.x;
-                                   acc.y += v.y * wn.y;
-                                   *q = acc;
+                                   *q = __ffma2_rn(v, wn, *q);
                                });
         if (!fold) fft_smem<PH, +1, T, 1, true>(Cz, tid, twh, ld_c, st_c);
 
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(128) col_fwd_kernel(const BandDev b, const Seg
         for (int r = 0; r < COL_R; r++) {
             const int n = r * N2 + n2;
             const float wn = __ldg(b.ana + n);
-            v[r] = make_float2(__ldg(pl + n) * wn, __ldg(pr + n) * wn);
+            v[r] = cscale(make_float2(__ldg(pl + n), __ldg(pr + n)), wn);
         }
     } else {
 #pragma unroll
@@ -615,8 +615,8 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
                 buf[hi] = yhi;
             }
             float2* cb = S + 4 * RS;
-            cb[lo] = make_float2(c[0].x - c[1].y, c[0].y + c[1].x);
-            cb[hi] = make_float2(c[0].x + c[1].y, c[1].x - c[0].y);
+            cb[lo] = cadd(c[0], make_float2(-c[1].y, c[1].x));                          // C_even + i C_odd
+            cb[hi] = cadd(make_float2(c[0].x, -c[0].y), make_float2(c[1].y, c[1].x));   // conj C_even + i conj C_odd
         }
     }
     __syncthreads();
@@ -713,8 +713,8 @@ __global__ void __launch_bounds__(N2 / 16, 65536 / (N2 / 16 * UPMIX_ROWP_REGS)) 
             sp[hi] = yhi;
         }
         float2* cb = spec + 8 * K;
-        cb[lo] = make_float2(c[0].x - c[1].y, c[0].y + c[1].x);
-        cb[hi] = make_float2(c[0].x + c[1].y, c[1].x - c[0].y);
+        cb[lo] = cadd(c[0], make_float2(-c[1].y, c[1].x));                          // C_even + i C_odd
+        cb[hi] = cadd(make_float2(c[0].x, -c[0].y), make_float2(c[1].y, c[1].x));   // conj C_even + i conj C_odd
         // row 0, point N2-K (slot K): the mirror of bin 16*K, which has no gain -- no item covers it, but
         // the pruned inverse reads it
         if (pr == 0 && tid == 0) spec[K] = spec[4 * K + K] = spec[8 * K + K] = make_float2(0.f, 0.f);
