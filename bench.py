@@ -7,7 +7,7 @@ audio-seconds processed per second, 48 kHz stereo).
 
 Workload (config.workload): BASELINE.json configs[1] -- a 1-hour 48 kHz stereo track, 3 bands
 (crossovers 0/200/2000 Hz -> STFT sizes 65536, 8192, 1024 by the dynamic-resolution rule), Ls/C/Rs
-out.  One step = one pass of the whole track through every band and the band sum.  With N > 1 every
+out.  One step = one pass of the whole track through every band, the bands summed in band order.  With N > 1 every
 rank runs its own 1-hour track (independent shards, no collective; "scaling": "weak") and `value`
 is the total audio-seconds of all ranks over the slowest rank's device time.
 
@@ -306,7 +306,7 @@ def main():
         except Exception:
             pass
         roofline = {"bound": "fp32", "kernel": f"band_fused_kernel<{dom_n}> (timed as the single-band plan of the N={dom_n} band: "
-                                               "this kernel + band_sum copy-out)",
+                                               "one launch of this kernel per step, writing its hops straight to the outputs)",
                     "achieved": dom_tflops, "peak": fp32_tflops, "unit": "TFLOP/s",
                     "frac": (dom_tflops / fp32_tflops) if dom_tflops else None, "traffic": traffic,
                     "traffic_note": "dram__bytes_read+write per launch scaled from profiles/traffic.json (ncu --set full)",

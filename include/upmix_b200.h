@@ -72,7 +72,8 @@ int upmix_plan_n_bands(const UpmixPlan* plan);
 int upmix_plan_n_pipelines(const UpmixPlan* plan);
 
 /* Bytes of device workspace upmix_process / upmix_process_segment need for seg_len output samples
- * per track and n_tracks tracks (negative on error).  Any 256-byte-aligned device buffer will do. */
+ * per track and n_tracks tracks (negative on error); the figure also covers every shorter segment with
+ * the same n_tracks.  Any 256-byte-aligned device buffer will do. */
 int64_t upmix_workspace_bytes(const UpmixPlan* plan, int64_t seg_len, int n_tracks);
 
 /* Whole tracks.  L, R: device, planar float32, track t at L + t*in_stride, n_samples each.

@@ -257,7 +257,7 @@ def test_unsupported_inputs_fail_loudly(ce):
         _native.Plan([(32, 8, w, w, np.ones(17, np.float32))])
 
 
-def test_pipelined_host_path_is_bit_identical(ce):
+def test_pipelined_host_path_is_bit_identical(ce, monkeypatch):
     """extract(..., pinned CPU tensors): segment-pipelined H2D / kernels / D2H == one device-resident call."""
     import torch
     sr = 48000
@@ -273,6 +273,12 @@ def test_pipelined_host_path_is_bit_identical(ce):
         assert not h.is_cuda and torch.equal(d.cpu(), h)
     host2 = plan.process_host_tensors(hl, hr, segment_seconds=7.0)
     for d, h in zip(dev, host2):
+        assert torch.equal(d.cpu(), h)
+    # full segments above the direct-sum threshold, a shorter last one below it (it stages its bands):
+    # one workspace sized for the full segment must serve both
+    monkeypatch.setenv("UPMIX_DIRECT_MIN", str(6 * sr))
+    host3 = plan.process_host_tensors(hl, hr, segment_seconds=7.0)
+    for d, h in zip(dev, host3):
         assert torch.equal(d.cpu(), h)
 
 

@@ -464,8 +464,17 @@ int upmix_plan_n_pipelines(const UpmixPlan* plan) { return plan ? (int)plan->ban
 int64_t upmix_workspace_bytes(const UpmixPlan* plan, int64_t seg_len, int n_tracks) {
     if (!plan) return fail(UPMIX_E_INVALID, "plan is NULL");
     if (seg_len < 0 || n_tracks < 1) return fail(UPMIX_E_INVALID, "bad seg_len / n_tracks");
-    // enough for either way of summing the bands at this size (block streaming always stages)
-    return make_layout(plan, seg_len, n_tracks, !direct_sum(seg_len, n_tracks)).total;
+    // Enough for this segment length AND any shorter one (callers size one workspace for a run of segments
+    // whose last one is shorter): long segments sum directly and need only the four-step scratch, which
+    // grows with the length; segments below the direct-sum threshold stage their bands, so the staged
+    // layout of the longest such segment is covered as well.
+    if (!direct_sum(seg_len, n_tracks)) return make_layout(plan, seg_len, n_tracks, true).total;
+    int64_t lo = 0, hi = seg_len;                      // largest staged length: direct_sum is monotonic in seg_len
+    while (lo < hi) {
+        const int64_t mid = lo + (hi - lo + 1) / 2;
+        if (direct_sum(mid, n_tracks)) hi = mid - 1; else lo = mid;
+    }
+    return std::max(make_layout(plan, seg_len, n_tracks, false).total, make_layout(plan, lo, n_tracks, true).total);
 }
 
 int64_t upmix_segment_halo(const UpmixPlan* plan) { return plan ? plan->halo : fail(UPMIX_E_INVALID, "plan is NULL"); }
