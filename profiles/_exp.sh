@@ -1,6 +1,3 @@
-python bench.py > gpurun_out/bench_r1c.json 2> gpurun_out/bench_r1c.err
-python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_r1c.json 2>> gpurun_out/bench_r1c.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1k.csv python profiles/profile_driver.py 1200 2 > gpurun_out/ncu_launch2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"band_fused|row_mask|col_" -c 5 -o gpurun_out/prof_r1k -f python profiles/profile_driver.py 600 1 > gpurun_out/ncu_full10.log 2>&1
-python profiles/config_bench.py > gpurun_out/config_bench2.txt 2>&1
-tail -c 300 gpurun_out/bench_r1c.err; cat gpurun_out/bench_r1c.json | head -c 1500
+python -m pytest tests -m gpu -x -q -s -k "every_size or fixture" 2>&1 | grep -E "passed|failed|^[0-9]+ \[|cfg" | cut -c1-220 | tail -20
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+for v in norec cur; do echo $v; if [ $v = cur ]; then unset UPMIX_B200_LIB; else export UPMIX_B200_LIB=$PWD/gpurun_variants/lib_$v.so; fi; python profiles/band_bench.py 3600 256:d 512:d 1024:d 2048:d 4096 8192:10 65536; python profiles/config_bench.py 2>&1 | grep "cfg2\|cfg1 shape\|cfg4"; done

@@ -18,6 +18,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef UPMIX_TW_RECUR
+#define UPMIX_TW_RECUR 1          // derive the non-power-of-two pass twiddles instead of loading them
+#endif
+
 namespace upmix {
 
 // Packed FP32x2 arithmetic (sm_100: add/mul/fma.f32x2, SASS FADD2 / FMUL2 / FFMA2).  The packed forms take
@@ -215,7 +219,8 @@ __device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2
             if (NS > 1) {                          // global loads first: they overlap the barrier
                 const float2* __restrict__ twp = tw + fft_tw_offset(PLAN, P) + k;
 #pragma unroll
-                for (int r = 1; r < R; r++) w[it][r] = __ldg(twp + (r - 1) * NS);
+                for (int r = 1; r < R; r++)
+                    if (!UPMIX_TW_RECUR || (r & (r - 1)) == 0) w[it][r] = __ldg(twp + (r - 1) * NS);
             }
             if (LAST) {
                 const int j0 = (j - k) * R + k;
@@ -242,6 +247,14 @@ __device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2
             if (NS > 1) {
 #pragma unroll
                 for (int r = 1; r < R; r++) {
+                    // w_r = w_1^r: only the powers of two are loaded, the rest is one packed complex multiply
+                    // away (w_r = w_{r - 2^q} w_{2^q}, at most log2 R - 1 roundings deep) -- the L1 / shared-
+                    // memory data pipe is the busiest unit of these kernels, the FMA pipe has room
+                    if (UPMIX_TW_RECUR && (r & (r - 1)) != 0) {
+                        int hb = 1;
+                        while (hb * 2 <= r) hb *= 2;
+                        w[it][r] = cmul(w[it][r - hb], w[it][hb]);
+                    }
                     float2 ww = w[it][r];
                     if (DIR > 0) ww.y = -ww.y;
                     v[it][r] = cmul(v[it][r], ww);
