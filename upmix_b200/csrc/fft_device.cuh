@@ -280,6 +280,16 @@ __device__ __forceinline__ void stockham_rec(float2* buf, int tid, const float2*
     if constexpr (P + 1 < fft_num_passes(PLAN)) stockham_rec<PLAN, P + 1, DIR, T, ROWS, LD_SMEM, Ld, St>(buf, tid, tw, ld, st);
 }
 
+// Passes P .. PEND-1 of a transform (the fused kernel runs the last forward pass and the first inverse pass
+// itself, fused with the centre mask).
+template <int PLAN, int P, int PEND, int DIR, int T, int ROWS, bool LD_SMEM, class Ld, class St>
+__device__ __forceinline__ void stockham_range(float2* buf, int tid, const float2* __restrict__ tw, Ld& ld, St& st) {
+    if constexpr (P < PEND) {
+        stockham_pass<PLAN, P, DIR, T, ROWS, LD_SMEM, Ld, St>(buf, tid, tw, ld, st);
+        stockham_range<PLAN, P + 1, PEND, DIR, T, ROWS, LD_SMEM, Ld, St>(buf, tid, tw, ld, st);
+    }
+}
+
 // Full transform of ROWS rows of fft_size(PLAN) points.  ld(row, n, it, r) supplies input point n; st
 // (a StoreFn) receives output point k (natural order).  LD_SMEM says ld reads the same shared buffer
 // (forces the read barrier).  tw = twiddle table of THIS plan (fft_tw_size(PLAN) entries).  Ends with
@@ -574,6 +584,228 @@ __device__ __forceinline__ void mask_bin_merged(float2 a, float2 b, float g0, co
         y_hi = cadd(y_hi, yh);
         c = cadd(c, cc);
     }
+}
+
+// z[k] = (C[k] + conj C[M-k]) + i e^{+2 pi i k/N} (C[k] - conj C[M-k]) and z[M-k], the packed spectrum whose
+// M-point inverse is c[2m] + i c[2m+1] (M = N/2; wk = exp(-2 pi i k / N)).
+__device__ __forceinline__ void pack_pair(float2 ck, float2 cmk, float2 wk, float2& zk, float2& zmk) {
+    const float2 A = cadd(ck, make_float2(cmk.x, -cmk.y));
+    const float2 B = cadd(ck, make_float2(-cmk.x, cmk.y));
+    const float2 D = cmul(B, make_float2(wk.x, -wk.y));
+    zk = cadd(A, make_float2(-D.y, D.x));
+    zmk = cadd(make_float2(A.x, -A.y), make_float2(D.y, D.x));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused middle of a frame: last forward pass -> split / gain / centre mask -> first pass of the inverse
+// transform of Ls + i Rs and of the packed centre, all in registers.
+//
+// The last forward pass (radix RL, NSL = N/RL butterflies) gives butterfly j the bins j + r NSL, and the
+// first pass of an inverse transform that starts with the same radix reads exactly those bins.  The mirror
+// of bin j + r NSL is (NSL - j) + (RL-1-r) NSL -- a bin of butterfly NSL - j -- so a thread that owns the
+// butterfly PAIR (j, NSL - j) holds every mirror pair the mask needs, and both inverse butterflies' inputs.
+// Bins k and M - k (M = N/2), which the packed centre spectrum combines, live in the same pair as well.
+// Thread 0 owns the two self-mirrored butterflies 0 and NSL/2 (bins 0 and N/2 are their own mirrors).
+// Against separate passes this saves, per frame, one store and two loads of the whole spectrum, one store
+// and one load of the centre spectrum, three barriers and the mask's index arithmetic: the kernels wait on
+// the shared-memory / L1 data pipe (81 % busy at 1024 points), not on arithmetic.
+//   Z:  spectrum buffer; read with the forward plan's padding, written with the inverse plan's
+//   Cz: packed centre spectrum (half plan's padding), written unless `fold`
+// MODE as band_fused_kernel.  Starts after the barrier of the previous forward pass, ends with a barrier.
+// ---------------------------------------------------------------------------------------------
+template <int N, int T, int PFW, int PIV, int PHV, bool MERGED, bool FUSE_HALF>
+__device__ __forceinline__ void mega_phase(float2* Z, float2* Cz, int tid, const float2* __restrict__ twf,
+                                           const float* __restrict__ gain, int n_gains, int gain_stride,
+                                           const float2* __restrict__ twp, bool fold) {
+    constexpr int PL = fft_num_passes(PFW) - 1;
+    constexpr int RL = fft_radix(PFW, PL);
+    constexpr int RH = RL / 2;
+    constexpr int NSL = N / RL;
+    constexpr int M = N / 2;
+    static_assert(fft_radix(PIV, 0) == RL && (!FUSE_HALF || fft_radix(PHV, 0) == RH) && 2 * T == NSL && RL >= 4, "plans do not line up");
+    const bool special = tid == 0;
+    const int j1 = tid, j2 = special ? NSL / 2 : NSL - tid;
+    float2 v1[RL], v2[RL], w1[RL], w2[RL], wp[RH];
+    float g[RL + 1];
+    int gk[RL + 1];                                      // bin of g[] (merged pipelines index more gain tables with it)
+    {   // everything that comes from global memory first
+        const float2* __restrict__ t1 = twf + fft_tw_offset(PFW, PL) + j1;
+        const float2* __restrict__ t2 = twf + fft_tw_offset(PFW, PL) + j2;
+#pragma unroll
+        for (int r = 1; r < RL; r++)
+            if (!UPMIX_TW_RECUR || (r & (r - 1)) == 0) {
+                w1[r] = __ldg(t1 + (r - 1) * NSL);
+                w2[r] = __ldg(t2 + (r - 1) * NSL);
+            }
+        if (!special) {
+#pragma unroll
+            for (int r = 0; r < RL; r++) {               // pair r: bins j1 + r NSL  <->  j2 + (RL-1-r) NSL
+                const int k = j1 + r * NSL;
+                gk[r] = k <= M ? k : N - k;
+                g[r] = __ldg(gain + gk[r]);
+            }
+            gk[RL] = 0;
+            g[RL] = 0.f;
+#pragma unroll
+            for (int r = 0; r < RH; r++) wp[r] = __ldg(twp + j1 + r * NSL);
+        } else {
+#pragma unroll
+            for (int r = 0; r <= RH; r++) {              // butterfly 0: bins r NSL <-> (RL-r) NSL
+                gk[r] = r * NSL;
+                g[r] = __ldg(gain + gk[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < RH; r++) {               // butterfly NSL/2: bins NSL/2 + r NSL <-> NSL/2 + (RL-1-r) NSL
+                gk[RH + 1 + r] = NSL / 2 + r * NSL;
+                g[RH + 1 + r] = __ldg(gain + gk[RH + 1 + r]);
+            }
+#pragma unroll
+            for (int r = 0; r < RH; r++)                 // k = (r+1) NSL for r < RL/4 (k = 0 needs none);  then k = NSL/2 + r' NSL
+                wp[r] = __ldg(twp + (r < RL / 4 ? (r + 1) * NSL : NSL / 2 + (r - RL / 4) * NSL));
+        }
+        const float2* __restrict__ s1 = Z + PAD<PFW>(j1);
+        const float2* __restrict__ s2 = Z + PAD<PFW>(j2);
+        constexpr int LD_STR = NSL + NSL / (1 << pad_shift(PFW));
+        static_assert(NSL % (1 << pad_shift(PFW)) == 0, "padded stride must be affine");
+#pragma unroll
+        for (int r = 0; r < RL; r++) {
+            v1[r] = s1[r * LD_STR];
+            v2[r] = s2[r * LD_STR];
+        }
+    }
+    __syncthreads();                                     // every read of Z before any write
+    // one butterfly after the other: the second one's twiddles need not be live during the first
+#pragma unroll
+    for (int r = 1; r < RL; r++) {
+        if (UPMIX_TW_RECUR && (r & (r - 1)) != 0) {
+            int hb = 1;
+            while (hb * 2 <= r) hb *= 2;
+            w1[r] = cmul(w1[r - hb], w1[hb]);
+        }
+        v1[r] = cmul(v1[r], w1[r]);
+    }
+    Dft<RL, -1>::run(v1);
+#pragma unroll
+    for (int r = 1; r < RL; r++) {
+        if (UPMIX_TW_RECUR && (r & (r - 1)) != 0) {
+            int hb = 1;
+            while (hb * 2 <= r) hb *= 2;
+            w2[r] = cmul(w2[r - hb], w2[hb]);
+        }
+        v2[r] = cmul(v2[r], w2[r]);
+    }
+    Dft<RL, -1>::run(v2);
+
+    // packed centre bins: zA[r] is bin j1 + r NSL, zB[r] bin j2 + r NSL -- the inputs of the half-size
+    // transform's first pass when it starts with radix RH (FUSE_HALF: kept in registers), otherwise
+    // stored at their natural place for a transform that runs all its passes
+    float2 zA[FUSE_HALF ? RH : 1], zB[FUSE_HALF ? RH : 1];
+    auto put_a = [&](int r, float2 z) {
+        if constexpr (FUSE_HALF) zA[r] = z;
+        else Cz[PAD<PHV>(j1 + r * NSL)] = z;
+    };
+    auto put_b = [&](int r, float2 z) {
+        if constexpr (FUSE_HALF) zB[r] = z;
+        else Cz[PAD<PHV>(j2 + r * NSL)] = z;
+    };
+    auto mask2 = [&](float2& a, float2& bb, int gi, float2& c) {     // mask one mirror pair in place
+        float2 ylo, yhi;
+        if constexpr (MERGED) mask_bin_merged(a, bb, g[gi], gain + gk[gi], n_gains, gain_stride, ylo, yhi, c);
+        else mask_bin(a, bb, g[gi], ylo, yhi, c);
+        if (fold) {                                      // (Ls + C/2) + i (Rs + C/2): add (1+i) C / 2
+            const float2 u = cadd(make_float2(c.x, c.x), make_float2(-c.y, c.y));
+            ylo = caxpy(u, 0.5f, ylo);
+            yhi = caxpy(make_float2(u.y, u.x), 0.5f, yhi);
+        }
+        a = ylo;
+        bb = yhi;
+    };
+    if (!special) {
+        // Pairs r and RH + r (bins k and k + M) feed the same packed-centre bins (k and M - k), so they are
+        // masked together, two such couples per step: four masks in flight, their centre values consumed
+        // at once.  A step whose four gains are all zero only clears its bins (most of a low band's spectrum).
+        constexpr int STEP = RH >= 2 ? 2 : 1;
+#pragma unroll
+        for (int r0 = 0; r0 < RH; r0 += STEP) {
+            bool any = false;
+#pragma unroll
+            for (int r = r0; r < r0 + STEP; r++) any = any || g[r] != 0.f || g[RH + r] != 0.f;
+            if (any) {
+#pragma unroll
+                for (int r = r0; r < r0 + STEP; r++) {
+                    float2 ca, cb;
+                    mask2(v1[r], v2[RL - 1 - r], r, ca);
+                    mask2(v1[RH + r], v2[RH - 1 - r], RH + r, cb);
+                    // C[M-k] = conj C[M+k], and bin M+k = j1 + (RH+r) NSL
+                    if (!fold) {
+                        float2 zk, zmk;
+                        pack_pair(ca, make_float2(cb.x, -cb.y), wp[r], zk, zmk);
+                        put_a(r, zk);
+                        put_b(RH - 1 - r, zmk);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = r0; r < r0 + STEP; r++) {
+                    v1[r] = v2[RL - 1 - r] = v1[RH + r] = v2[RH - 1 - r] = make_float2(0.f, 0.f);
+                    if (!fold) {
+                        put_a(r, make_float2(0.f, 0.f));
+                        put_b(RH - 1 - r, make_float2(0.f, 0.f));
+                    }
+                }
+            }
+        }
+    } else {
+        float2 c1[RH + 1], c2[RH];
+        {
+            float2 t = v1[0];
+            mask2(v1[0], t, 0, c1[0]);                   // bin 0 is its own mirror
+            t = v1[RH];
+            mask2(v1[RH], t, RH, c1[RH]);                // so is bin N/2
+        }
+#pragma unroll
+        for (int r = 1; r < RH; r++) mask2(v1[r], v1[RL - r], r, c1[r]);
+#pragma unroll
+        for (int r = 0; r < RH; r++) mask2(v2[r], v2[RL - 1 - r], RH + 1 + r, c2[r]);
+        if (!fold) {
+#pragma unroll
+            for (int r = 0; r <= RL / 4; r++) {          // k = r NSL, M - k = (RH - r) NSL
+                float2 zk, zmk;
+                pack_pair(c1[r], c1[RH - r], r == 0 ? make_float2(1.f, 0.f) : wp[r - 1], zk, zmk);
+                put_a(r, zk);
+                if (r > 0) put_a(RH - r, zmk);
+            }
+#pragma unroll
+            for (int r = 0; r < RL / 4; r++) {           // k = NSL/2 + r NSL, M - k = NSL/2 + (RH-1-r) NSL
+                float2 zk, zmk;
+                pack_pair(c2[r], c2[RH - 1 - r], wp[RL / 4 + r], zk, zmk);
+                put_b(r, zk);
+                put_b(RH - 1 - r, zmk);
+            }
+        }
+    }
+
+    Dft<RL, +1>::run(v1);                                // first inverse pass: no twiddles, outputs j RL + r
+    Dft<RL, +1>::run(v2);
+    float2* __restrict__ d1 = Z + PAD<PIV>(j1 * RL);
+    float2* __restrict__ d2 = Z + PAD<PIV>(j2 * RL);
+#pragma unroll
+    for (int r = 0; r < RL; r++) {
+        d1[r] = v1[r];
+        d2[r] = v2[r];
+    }
+    if (FUSE_HALF && !fold) {
+        Dft<FUSE_HALF ? RH : 1, +1>::run(zA);
+        Dft<FUSE_HALF ? RH : 1, +1>::run(zB);
+        float2* __restrict__ e1 = Cz + PAD<PHV>(j1 * RH);
+        float2* __restrict__ e2 = Cz + PAD<PHV>(j2 * RH);
+#pragma unroll
+        for (int r = 0; r < (FUSE_HALF ? RH : 1); r++) {
+            e1[r] = zA[r];
+            e2[r] = zB[r];
+        }
+    }
+    __syncthreads();
 }
 
 }  // namespace upmix

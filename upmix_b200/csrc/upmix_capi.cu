@@ -318,10 +318,10 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
         if (d.n_fft > FUSED_MAX_N) {
             floats += 2LL * d.n_fft + round_up(2LL * fft_tw_size(row_plan(d.n_fft / COL_R)), 64);
         } else {
-            int pf = 0, ph = 0;
-            fused_plans(d.n_fft, &pf, &ph);
-            floats += round_up(2LL * fft_tw_size(pf), 64) + round_up(2LL * fft_tw_size(ph), 64) +
-                      round_up(2LL * (d.n_fft / 4 + 1), 64);
+            int pf = 0, pi = 0, ph = 0;
+            fused_plans(d.n_fft, &pf, &pi, &ph);
+            floats += round_up(2LL * fft_tw_size(pf), 64) + round_up(2LL * fft_tw_size(pi), 64) +
+                      round_up(2LL * fft_tw_size(ph), 64) + round_up(2LL * (d.n_fft / 2), 64);
         }
     }
     DeviceGuard guard(device);
@@ -358,7 +358,7 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
         BandDev b;
         b.n_fft = d.n_fft;
         b.hop = d.hop;
-        b.tw_fft = b.tw_half = b.tw_pack = b.tw_col = nullptr;
+        b.tw_fft = b.tw_inv = b.tw_half = b.tw_pack = b.tw_col = nullptr;
         memcpy(&host[off], d.ana, sizeof(float) * d.n_fft);      // ana[n_fft] = 0 follows (host is zero-filled)
         b.ana = dbase + off;
         off += round_up(d.n_fft + 1, 64);
@@ -385,21 +385,24 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
             off += ng * gs;
         }
         if (d.n_fft <= FUSED_MAX_N) {
-            int pf = 0, ph = 0;
-            fused_plans(d.n_fft, &pf, &ph);
+            int pf = 0, pi = 0, ph = 0;
+            fused_plans(d.n_fft, &pf, &pi, &ph);
             gen_fft_tw(pf, &host[off]);
             b.tw_fft = reinterpret_cast<const float2*>(dbase + off);
             off += round_up(2LL * fft_tw_size(pf), 64);
+            gen_fft_tw(pi, &host[off]);
+            b.tw_inv = reinterpret_cast<const float2*>(dbase + off);
+            off += round_up(2LL * fft_tw_size(pi), 64);
             gen_fft_tw(ph, &host[off]);
             b.tw_half = reinterpret_cast<const float2*>(dbase + off);
             off += round_up(2LL * fft_tw_size(ph), 64);
-            for (int k = 0; k <= d.n_fft / 4; k++) {
+            for (int k = 0; k < d.n_fft / 2; k++) {
                 const double ang = -2.0 * M_PI * (double)k / (double)d.n_fft;
                 host[off + 2 * k] = (float)cos(ang);
                 host[off + 2 * k + 1] = (float)sin(ang);
             }
             b.tw_pack = reinterpret_cast<const float2*>(dbase + off);
-            off += round_up(2LL * (d.n_fft / 4 + 1), 64);
+            off += round_up(2LL * (d.n_fft / 2), 64);
         } else {
             const int n2 = d.n_fft / COL_R;
             gen_fft_tw(row_plan(n2), &host[off]);

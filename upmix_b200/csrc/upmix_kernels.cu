@@ -39,50 +39,67 @@ namespace upmix {
 #define UPMIX_TMA_MIN_N 2048      // frames of this size and larger are staged by TMA bulk copies
 #endif
 template <int N> struct FusedCfg;
+#ifndef UPMIX_MEGA
+#define UPMIX_MEGA 1              // fuse last forward pass, mask and first inverse passes (mega_phase) where the plans line up
+#endif
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
 #define UPMIX_FUSED_CFG_X(N_, ...) UPMIX_FUSED_CFG(N_, __VA_ARGS__)
-#define UPMIX_FUSED_CFG(N_, FULL_, HALF_, T_, MINB_)                                                     \
+#define UPMIX_FUSED_CFG(N_, FWD_, INV_, HALF_, T_, MINB_)                                                \
     template <> struct FusedCfg<N_> {                                                                     \
-        static constexpr int FULL = FULL_, HALF = HALF_, T = T_, MINB = MINB_;                            \
+        static constexpr int FWD = FWD_, INV = INV_, HALF = HALF_, T = T_, MINB = MINB_;                  \
         static constexpr bool TMA = N_ >= UPMIX_TMA_MIN_N;                                               \
+        /* the fused middle needs: inverse starts with the forward's last radix RL, the half transform   \
+           with RL/2, and one butterfly pair per thread */                                               \
+        static constexpr int RL = fft_radix(FWD_, fft_num_passes(FWD_) - 1);                              \
+        static constexpr bool MEGA = UPMIX_MEGA && RL >= 4 && fft_radix(INV_, 0) == RL && 2 * T_ * RL == N_; \
+        static constexpr bool FUSE_HALF = MEGA && 2 * fft_radix(HALF_, 0) == RL;                          \
         /* registers per thread: the share of the file MINB co-resident CTAs leave, but never the whole \
            file for one CTA -- UPMIX_REG_CAP keeps room for CTAs of other pipelines on the same SM */ \
         static constexpr int MAXREG = (65536 / (T_ * MINB_) / 8 * 8) > UPMIX_REG_CAP ? UPMIX_REG_CAP : (65536 / (T_ * MINB_) / 8 * 8);                            \
-        static_assert(fft_size(FULL_) == N_ && fft_size(HALF_) == N_ / 2, "plan does not match the size"); \
-        static constexpr int SMEM = (PADSZ<FULL_>() + PADSZ<HALF_>()) * (int)sizeof(float2) + 3 * N_ * (int)sizeof(float); \
+        static_assert(fft_size(FWD_) == N_ && fft_size(INV_) == N_ && fft_size(HALF_) == N_ / 2, "plan does not match the size"); \
+        static constexpr int ZSZ = cmax(PADSZ<FWD_>(), PADSZ<INV_>());                                    \
+        static constexpr int SMEM = (ZSZ + PADSZ<HALF_>()) * (int)sizeof(float2) + 3 * N_ * (int)sizeof(float); \
     };
 // Chosen by measurement on B200 (profiles/band_bench.py; see profiles/r01_tuning.md): 16-32 points per
-// thread, every lane busy in every pass, a radix-32 first pass from 2048 points up (three passes), and
-// enough registers to avoid spills even if that leaves 8-12 warps per SM.
+// thread, every lane busy in every pass, and enough registers to avoid spills even if that leaves 8-12
+// warps per SM.  Fields: forward plan, inverse plan, half-size plan, threads, CTAs per SM.  From 256 points
+// up the forward plan ends with the radix RL = points per thread / 2, the inverse plan starts with it and the
+// half plan with RL/2, so the middle of the frame runs fused in registers (mega_phase).  Measured, ms per
+// band-hour, separate passes with the previous plans / fused middle / fused middle but the half-size
+// transform on its own (its spectrum stored, any plan): 256: 6.81 / 5.91 / 5.91; 512: 5.15 / 5.52 / 5.79;
+// 1024: 5.09 / 6.04 / 5.40; 2048: 5.80 / 5.60 / 5.75; 4096: 5.77 / 5.67 / 5.64; 8192: 6.49 / 8.10 (spills) /
+// 6.24.  512 and 1024 points (16 points per thread, RL = 8) keep the separate passes: their best plans
+// end with a cheap radix-4 pass, which the fusion cannot use.
 #ifndef UPMIX_CFG_64
-#define UPMIX_CFG_64 mkplan(8, 8), mkplan(8, 4), 32, 16
+#define UPMIX_CFG_64 mkplan(8, 8), mkplan(8, 8), mkplan(8, 4), 32, 16
 #endif
 UPMIX_FUSED_CFG_X(64, UPMIX_CFG_64)
 #ifndef UPMIX_CFG_128
-#define UPMIX_CFG_128 mkplan(8, 4, 4), mkplan(4, 4, 4), 32, 16
+#define UPMIX_CFG_128 mkplan(8, 4, 4), mkplan(8, 4, 4), mkplan(4, 4, 4), 32, 16
 #endif
 UPMIX_FUSED_CFG_X(128, UPMIX_CFG_128)
 #ifndef UPMIX_CFG_256
-#define UPMIX_CFG_256 mkplan(8, 8, 4), mkplan(4, 4, 8), 32, 12
+#define UPMIX_CFG_256 mkplan(8, 8, 4), mkplan(4, 8, 8), mkplan(2, 8, 8), 32, 12
 #endif
 UPMIX_FUSED_CFG_X(256, UPMIX_CFG_256)
 #ifndef UPMIX_CFG_512
-#define UPMIX_CFG_512 mkplan(16, 8, 4), mkplan(8, 8, 4), 32, 16
+#define UPMIX_CFG_512 mkplan(16, 8, 4), mkplan(16, 8, 4), mkplan(8, 8, 4), 32, 16
 #endif
 UPMIX_FUSED_CFG_X(512, UPMIX_CFG_512)
 #ifndef UPMIX_CFG_1024
-#define UPMIX_CFG_1024 mkplan(16, 16, 4), mkplan(16, 8, 4), 64, 6
+#define UPMIX_CFG_1024 mkplan(16, 16, 4), mkplan(16, 16, 4), mkplan(16, 8, 4), 64, 6
 #endif
 UPMIX_FUSED_CFG_X(1024, UPMIX_CFG_1024)
 #ifndef UPMIX_CFG_2048
-#define UPMIX_CFG_2048 mkplan(32, 8, 8), mkplan(16, 16, 4), 64, 4
+#define UPMIX_CFG_2048 mkplan(16, 8, 16), mkplan(16, 8, 16), mkplan(8, 8, 16), 64, 4
 #endif
 UPMIX_FUSED_CFG_X(2048, UPMIX_CFG_2048)
 #ifndef UPMIX_CFG_4096
-#define UPMIX_CFG_4096 mkplan(32, 16, 8), mkplan(16, 16, 8), 128, 2
+#define UPMIX_CFG_4096 mkplan(16, 16, 16), mkplan(16, 16, 16), mkplan(16, 16, 8), 128, 2
 #endif
 UPMIX_FUSED_CFG_X(4096, UPMIX_CFG_4096)
 #ifndef UPMIX_CFG_8192
-#define UPMIX_CFG_8192 mkplan(32, 16, 16), mkplan(16, 16, 16), 256, 1
+#define UPMIX_CFG_8192 mkplan(32, 16, 16), mkplan(16, 16, 32), mkplan(16, 16, 16), 256, 1
 #endif
 UPMIX_FUSED_CFG_X(8192, UPMIX_CFG_8192)
 
@@ -94,10 +111,11 @@ template <int N, int MODE>
 __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXREG) band_fused_kernel(const BandDev b, const SegArgs a) {
     constexpr int T = FusedCfg<N>::T;
     constexpr int M = N / 2;
-    constexpr int PF = FusedCfg<N>::FULL, PH = FusedCfg<N>::HALF;
+    constexpr int PF = FusedCfg<N>::FWD, PI = FusedCfg<N>::INV, PH = FusedCfg<N>::HALF;
+    constexpr bool MEGA = FusedCfg<N>::MEGA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* Z = reinterpret_cast<float2*>(smem_raw);
-    float2* Cz = Z + PADSZ<PF>();
+    float2* Cz = Z + FusedCfg<N>::ZSZ;
     float* ring = reinterpret_cast<float*>(Cz + PADSZ<PH>());   // [3][N]: C, Ls, Rs
 
     const int tid = threadIdx.x;
@@ -132,6 +150,7 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
     const float* __restrict__ syn = b.syn;
     const float* __restrict__ gain = b.gain;
     const float2* __restrict__ tw = b.tw_fft;
+    const float2* __restrict__ twi = b.tw_inv;
     const float2* __restrict__ twh = b.tw_half;
     const float2* __restrict__ twp = b.tw_pack;
 
@@ -252,18 +271,24 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
         // (small sizes run 16 CTAs per SM on a 128-register budget: they load at the copy-out instead)
         const bool pre = N >= 1024 && accum && vec_out && H <= 4 * T * ITE;
         float4 prev[3][ITE];
-        if (pre) {
+        auto request_prev = [&]() {
+            if (pre) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                if (ch == 0 && fold) continue;
-                const float* __restrict__ po = outp[ch] + (s0 - a.out_begin);
+                for (int ch = 0; ch < 3; ch++) {
+                    if (ch == 0 && fold) continue;
+                    const float* __restrict__ po = outp[ch] + (s0 - a.out_begin);
 #pragma unroll
-                for (int it = 0; it < ITE; it++) {
-                    const int i = (tid + it * T) * 4;
-                    if (i < H) prev[ch][it] = __ldcs(reinterpret_cast<const float4*>(po + i));
+                    for (int it = 0; it < ITE; it++) {
+                        const int i = (tid + it * T) * 4;
+                        if (i < H) prev[ch][it] = __ldcs(reinterpret_cast<const float4*>(po + i));
+                    }
                 }
             }
-        }
+        };
+        // 16 points per thread: 12 registers held through the whole frame; 32 points per thread: 24, requested
+        // once the fused middle of the frame (the register peak) is over
+        constexpr bool PREV_AT_TOP = N <= 1024;
+        if (PREV_AT_TOP) request_prev();
 
         // ---- forward: Z = FFT_N( ana * (L + iR) ) -----------------------------------------------
         if (TMA && in_by_tma) {
@@ -276,6 +301,11 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
             else return cscale(xin[it][r], wn);
         };
         auto st_z = make_store([&](int, int k, float2 v, NoAux) { Z[PAD<PF>(k)] = v; });
+        if constexpr (MEGA) {
+            // all forward passes but the last; the last one runs fused with the mask and the first inverse passes
+            stockham_range<PF, 0, fft_num_passes(PF) - 1, -1, T, 1, TMA>(Z, tid, tw, ld_in, st_z);
+            mega_phase<N, T, PF, PI, PH, MODE == MODE_MERGED, FusedCfg<N>::FUSE_HALF>(Z, Cz, tid, tw, gain, b.n_gains, b.gain_stride, twp, fold);
+        } else {
         fft_smem<PF, -1, T, 1, TMA>(Z, tid, tw, ld_in, st_z);      // TMA: in place, SL/SR live inside Z
 
         // ---- split / gain / mask; Y1 = Ls + i*Rs in place, C packed for the half-size inverse ---
@@ -378,6 +408,9 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
             }
         }
         __syncthreads();
+        }   // !MEGA
+
+        if (!PREV_AT_TOP) request_prev();
 
         // ---- inverse transforms, synthesis window, overlap-add (oldest frame first) --------------
         auto ld_z = [&](int, int n, int, int) -> float2 { return Z[PAD<PF>(n)]; };
@@ -388,7 +421,8 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
                                     ring[N + p] = acc.x;
                                     ring[2 * N + p] = acc.y;
                                 });
-        fft_smem<PF, +1, T, 1, true>(Z, tid, tw, ld_z, st_lr);
+        if constexpr (MEGA) stockham_range<PI, 1, fft_num_passes(PI), +1, T, 1, true>(Z, tid, twi, ld_z, st_lr);
+        else fft_smem<PF, +1, T, 1, true>(Z, tid, tw, ld_z, st_lr);
         if (TMA && f + 1 < h1) stage(f + 1);       // Z is idle from here to the next frame's first pass
         auto ld_c = [&](int, int n, int, int) -> float2 { return Cz[PAD<PH>(n)]; };
         auto st_c = make_store([&](int, int m) -> float2 { return __ldg(reinterpret_cast<const float2*>(syn) + m); },
@@ -397,7 +431,10 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
                                    float2* q = reinterpret_cast<float2*>(ring + p);
                                    *q = __ffma2_rn(v, wn, *q);
                                });
-        if (!fold) fft_smem<PH, +1, T, 1, true>(Cz, tid, twh, ld_c, st_c);
+        if (!fold) {
+            if constexpr (FusedCfg<N>::FUSE_HALF) stockham_range<PH, 1, fft_num_passes(PH), +1, T, 1, true>(Cz, tid, twh, ld_c, st_c);
+            else fft_smem<PH, +1, T, 1, true>(Cz, tid, twh, ld_c, st_c);
+        }
 
         if (!TMA && f + 1 < h1) stage(f + 1);      // register variant: request the next frame before the copy-out
 
@@ -1207,10 +1244,10 @@ cudaError_t launch_band_fused(const BandDev& b, const SegArgs& a, int n_runs, in
 }
 
 // radix plans, for the host-side twiddle tables
-void fused_plans(int n_fft, int* full, int* half) {
-    *full = *half = 0;
+void fused_plans(int n_fft, int* fwd, int* inv, int* half) {
+    *fwd = *inv = *half = 0;
     switch (n_fft) {
-#define UPMIX_CASE(N_) case N_: *full = FusedCfg<N_>::FULL; *half = FusedCfg<N_>::HALF; break;
+#define UPMIX_CASE(N_) case N_: *fwd = FusedCfg<N_>::FWD; *inv = FusedCfg<N_>::INV; *half = FusedCfg<N_>::HALF; break;
         UPMIX_CASE(64) UPMIX_CASE(128) UPMIX_CASE(256) UPMIX_CASE(512) UPMIX_CASE(1024) UPMIX_CASE(2048)
         UPMIX_CASE(4096) UPMIX_CASE(8192)
 #undef UPMIX_CASE

@@ -26,8 +26,10 @@ struct BandDev {
     int max_bin;               // highest bin with a non-zero gain in any of the merged bands (-1: none)
     const float2* tw_fft;      // per-pass twiddles (fft_device.cuh layout) of the n_fft-point transform
                                // (fused path) or of the n_fft/16-point row transform (large path)
+    const float2* tw_inv;      // per-pass twiddles of the inverse n_fft-point transform's plan (fused path; the
+                               // fused kernel's inverse starts with the radix its forward transform ends with)
     const float2* tw_half;     // per-pass twiddles of the n_fft/2-point transform (fused path)
-    const float2* tw_pack;     // [n_fft/4+1]   exp(-2*pi*i*k/n_fft) for the real-signal packing (fused path)
+    const float2* tw_pack;     // [n_fft/2]     exp(-2*pi*i*k/n_fft) for the real-signal packing (fused path)
     const float2* tw_col;      // [16][n_fft/16] exp(-2*pi*i*k1*n2/n_fft), large path only
 };
 

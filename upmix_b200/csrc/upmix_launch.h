@@ -7,7 +7,7 @@ namespace upmix {
 
 cudaError_t launch_band_fused(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st);
 int fused_smem_bytes(int n_fft);
-void fused_plans(int n_fft, int* full, int* half);
+void fused_plans(int n_fft, int* fwd, int* inv, int* half);
 int row_plan(int n2);
 int fused_ctas_per_sm(int n_fft);
 cudaError_t launch_col_fwd(const BandDev& b, const SegArgs& a, const WaveArgs& w, int n_tracks, cudaStream_t st);
