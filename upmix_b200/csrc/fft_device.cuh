@@ -105,6 +105,23 @@ struct Dft<1, DIR> {
 
 __host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 
+// v[k] *= w^k (CONJ: conj(w)^k), k = 1..15, from the four loaded powers w^1, w^2, w^4, w^8: every other power
+// is a product of at most four of them, so the rounding stays within a few ulp of a table look-up while
+// eleven of fifteen loads go away (the four-step twiddles W_N^{k1 n2} of one column n2).
+template <bool CONJ>
+__device__ __forceinline__ void apply_powers16(float2 (&v)[16], float2 w1, float2 w2, float2 w4, float2 w8) {
+    float2 w[16];
+    w[1] = w1; w[2] = w2; w[4] = w4; w[8] = w8;
+    w[3] = cmul(w1, w2);
+    w[5] = cmul(w1, w4);
+    w[6] = cmul(w2, w4);
+    w[7] = cmul(w[3], w4);
+#pragma unroll
+    for (int k = 9; k < 16; k++) w[k] = cmul(w[k - 8], w8);
+#pragma unroll
+    for (int k = 1; k < 16; k++) v[k] = cmul(v[k], CONJ ? make_float2(w[k].x, -w[k].y) : w[k]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers: one elected thread moves a frame's
 // samples global -> shared asynchronously; consumers wait on the mbarrier's phase parity.

@@ -27,7 +27,12 @@ namespace upmix {
 // Per-size configuration of the fused kernel: radix plans of the N-point and N/2-point transforms,
 // threads per CTA (= per frame in flight) and the CTAs per SM the register budget is sized for.
 #ifndef UPMIX_TW_IN_ROW
-#define UPMIX_TW_IN_ROW 1     // four-step twiddles applied by the row kernel (1) or by the column kernels (0)
+#define UPMIX_TW_IN_ROW -1    // four-step twiddles applied by the row kernel (1: one table look-up per point, as
+                              // much L2 traffic as the data) or by the column kernels (0: a column's fifteen
+                              // twiddles are powers of one number -- four look-ups, eleven multiplies); -1: by
+                              // size, as measured (ms per band-hour, row / column): 16384 6.56 / 6.88-6.97,
+                              // 32768 6.34 / 6.22, 65536 6.55 / 6.14 -- short rows leave the column kernels,
+                              // which sit at the HBM roofline, as the larger share
 #endif
 #ifndef UPMIX_REG_CAP
 #define UPMIX_REG_CAP 255
@@ -38,6 +43,8 @@ namespace upmix {
 #ifndef UPMIX_TMA_MIN_N
 #define UPMIX_TMA_MIN_N 2048      // frames of this size and larger are staged by TMA bulk copies
 #endif
+static inline bool tw_in_row(int n_fft) { return UPMIX_TW_IN_ROW < 0 ? n_fft / COL_R <= 1024 : UPMIX_TW_IN_ROW != 0; }
+
 template <int N> struct FusedCfg;
 #ifndef UPMIX_MEGA
 #define UPMIX_MEGA 1              // fuse last forward pass, mask and first inverse passes (mega_phase) where the plans line up
@@ -509,6 +516,7 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
 // ---------------------------------------------------------------------------------------------
 // K1: one thread per (frame, column n2): windowed samples x[16 rows][n2] -> radix-16 DFT over the
 // rows -> A[frame][k1][n2] (the four-step twiddle W_N^{n2*k1} is applied by the row kernel's loads).
+template <bool TWROW>
 __global__ void __launch_bounds__(128) col_fwd_kernel(const BandDev b, const SegArgs a, const WaveArgs w) {
     const int N2 = b.n_fft / COL_R;
     const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -543,14 +551,11 @@ __global__ void __launch_bounds__(128) col_fwd_kernel(const BandDev b, const Seg
     }
     Dft<COL_R, -1>::run(v);
     float2* dst = w.a + (((long long)track * w.n_frames + fl) * COL_R) * N2 + n2;
-#if UPMIX_TW_IN_ROW
+    if constexpr (!TWROW)          // A * W_N^{k1 n2} here; otherwise the row kernel applies it
+        apply_powers16<false>(v, __ldg(b.tw_col + N2 + n2), __ldg(b.tw_col + 2 * N2 + n2), __ldg(b.tw_col + 4 * N2 + n2),
+                              __ldg(b.tw_col + 8 * N2 + n2));
 #pragma unroll
-    for (int k1 = 0; k1 < COL_R; k1++) dst[(long long)k1 * N2] = v[k1];     // twiddled by the row kernel
-#else
-    dst[0] = v[0];
-#pragma unroll
-    for (int k1 = 1; k1 < COL_R; k1++) dst[(long long)k1 * N2] = cmul(v[k1], __ldg(b.tw_col + k1 * N2 + n2));
-#endif
+    for (int k1 = 0; k1 < COL_R; k1++) dst[(long long)k1 * N2] = v[k1];
 }
 
 template <int N2> struct RowCfg;
@@ -578,7 +583,7 @@ UPMIX_ROW_CFG(4096, UPMIX_ROWPLAN_4096)
 // mirror images of each other (bin k <-> N-k), so the CTA holds both rows of both frames, finishes
 // the forward transform along the rows, applies split/gain/mask, and starts the inverse transform
 // (rows) of Ls+iRs for each frame and of C(even frame) + i*C(odd frame).
-template <int N2>
+template <int N2, bool TWROW>
 __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b, const WaveArgs w) {
     constexpr int T = RowCfg<N2>::T;
     constexpr int PL = RowCfg<N2>::PLAN;
@@ -601,11 +606,8 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
     for (int g = 0; g < 2; g++) {
         auto ld = [&](int row, int n, int, int) -> float2 {      // A * W_N^{k1 n}: the four-step twiddle
             const int k1 = row ? kb : ka;
-#if UPMIX_TW_IN_ROW
-            return cmul(A[(fbase + (long long)g * COL_R + k1) * N2 + n], __ldg(twc + k1 * N2 + n));
-#else
-            return A[(fbase + (long long)g * COL_R + k1) * N2 + n];
-#endif
+            if constexpr (TWROW) return cmul(A[(fbase + (long long)g * COL_R + k1) * N2 + n], __ldg(twc + k1 * N2 + n));
+            else return A[(fbase + (long long)g * COL_R + k1) * N2 + n];
         };
         float2* buf = S + 2 * g * RS;
         auto st = make_store([&](int row, int k, float2 v, NoAux) { buf[row * RS + PAD<PL>(k)] = v; });
@@ -665,16 +667,17 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
         auto ld = [&](int row, int n, int, int) -> float2 { return buf[row * RS + PAD<PL>(n)]; };
         float2* dst = g < 2 ? w.b1 + (fbase + (long long)g * COL_R) * N2
                             : w.b2 + (((long long)track * (w.n_frames / 2) + fp) * COL_R) * N2;
-#if UPMIX_TW_IN_ROW
-        auto st = make_store([&](int row, int n) -> float2 { return __ldg(twc + (row ? kb : ka) * N2 + n); },
-                             [&](int row, int n, float2 v, float2 t) {     // * conj W_N^{k1 n}
-                                 const int k1 = row ? kb : ka;
-                                 dst[(long long)k1 * N2 + n] = cmul(v, make_float2(t.x, -t.y));
-                             });
-#else
-        auto st = make_store([&](int row, int n, float2 v, NoAux) { dst[(long long)(row ? kb : ka) * N2 + n] = v; });
-#endif
-        fft_smem<PL, +1, T, 2, true>(buf, tid, tw, ld, st);
+        if constexpr (TWROW) {
+            auto st = make_store([&](int row, int n) -> float2 { return __ldg(twc + (row ? kb : ka) * N2 + n); },
+                                 [&](int row, int n, float2 v, float2 t) {     // * conj W_N^{k1 n}
+                                     const int k1 = row ? kb : ka;
+                                     dst[(long long)k1 * N2 + n] = cmul(v, make_float2(t.x, -t.y));
+                                 });
+            fft_smem<PL, +1, T, 2, true>(buf, tid, tw, ld, st);
+        } else {
+            auto st = make_store([&](int row, int n, float2 v, NoAux) { dst[(long long)(row ? kb : ka) * N2 + n] = v; });
+            fft_smem<PL, +1, T, 2, true>(buf, tid, tw, ld, st);
+        }
     }
 }
 
@@ -689,7 +692,7 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 #ifndef UPMIX_ROWP_REGS
 #define UPMIX_ROWP_REGS 128       // register budget per thread: 65536 / (T * REGS) CTAs share an SM
 #endif
-template <int N2>
+template <int N2, bool TWROW>
 __global__ void __launch_bounds__(N2 / 16, 65536 / (N2 / 16 * UPMIX_ROWP_REGS)) row_mask_pruned_kernel(const BandDev b, const WaveArgs w) {
     constexpr int T = N2 / 16;
     constexpr int PL = RowCfg<N2>::PLAN;
@@ -714,7 +717,10 @@ __global__ void __launch_bounds__(N2 / 16, 65536 / (N2 / 16 * UPMIX_ROWP_REGS)) 
         const int g = s >> 1, k1 = (s & 1) ? kb : ka;
         const float2* __restrict__ src = A + (fbase + (long long)g * COL_R + k1) * N2;
         const float2* __restrict__ twr = twc + k1 * N2;
-        auto ld = [&](int, int n, int, int) -> float2 { return cmul(src[n], __ldg(twr + n)); };   // * W_N^{k1 n}
+        auto ld = [&](int, int n, int, int) -> float2 {
+            if constexpr (TWROW) return cmul(src[n], __ldg(twr + n));       // * W_N^{k1 n}
+            else return src[n];                                             // twiddled by col_fwd
+        };
         float2* sp = spec + s * 2 * K;
         auto out = [&](int, int idx, float2 v) { sp[idx] = v; };
         fft_rows_fwd_pruned<PL, T, 1>(buf, tid, tw, ld, out);
@@ -766,9 +772,14 @@ __global__ void __launch_bounds__(N2 / 16, 65536 / (N2 / 16 * UPMIX_ROWP_REGS)) 
         const float2* __restrict__ twr = twc + k1 * N2;
         const float2* sp = spec + s * 2 * K;
         auto in = [&](int, int idx) -> float2 { return sp[idx]; };
-        auto st = make_store([&](int, int n) -> float2 { return __ldg(twr + n); },
-                             [&](int, int n, float2 v, float2 t) { dst[n] = cmul(v, make_float2(t.x, -t.y)); });   // * conj W_N^{k1 n}
-        fft_rows_inv_pruned<PL, T, 1>(buf, tid, tw, in, st);
+        if constexpr (TWROW) {
+            auto st = make_store([&](int, int n) -> float2 { return __ldg(twr + n); },
+                                 [&](int, int n, float2 v, float2 t) { dst[n] = cmul(v, make_float2(t.x, -t.y)); });   // * conj W_N^{k1 n}
+            fft_rows_inv_pruned<PL, T, 1>(buf, tid, tw, in, st);
+        } else {
+            auto st = make_store([&](int, int n, float2 v, NoAux) { dst[n] = v; });               // twiddled by col_inv_ola
+            fft_rows_inv_pruned<PL, T, 1>(buf, tid, tw, in, st);
+        }
     }
 }
 
@@ -776,7 +787,10 @@ __global__ void __launch_bounds__(N2 / 16, 65536 / (N2 / 16 * UPMIX_ROWP_REGS)) 
 // frames before it whose tails reach into the run) the thread finishes the inverse transform down
 // its column (radix-16), applies the synthesis window and overlap-adds in registers: a frame shifts
 // the 16-row accumulator by 4 rows (hop = N/4 = 4*N2), the 4 rows that fall out are finished samples.
-__global__ void __launch_bounds__(128, 4) col_inv_ola_kernel(const BandDev b, const SegArgs a, const WaveArgs w) {
+// TWROW = false: the kernel also applies the four-step twiddles, which costs registers: 3 CTAs per SM (168
+// registers, no spills) instead of 4 (measured: 65536 6.70 -> 6.14 ms per band-hour)
+template <bool TWROW>
+__global__ void __launch_bounds__(128, TWROW ? 4 : 3) col_inv_ola_kernel(const BandDev b, const SegArgs a, const WaveArgs w) {
     const int N2 = b.n_fft / COL_R;
     const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
     if (n2 >= N2) return;
@@ -795,6 +809,14 @@ __global__ void __launch_bounds__(128, 4) col_inv_ola_kernel(const BandDev b, co
     for (int ch = 0; ch < 3; ch++)
 #pragma unroll
         for (int i = 0; i < COL_R; i++) acc[ch][i] = 0.f;
+    // this column's four-step twiddles W_N^{k1 n2}: four powers kept, the rest rebuilt before every column transform
+    float2 tw1, tw2, tw4, tw8;
+    if constexpr (!TWROW) {
+        tw1 = __ldg(b.tw_col + N2 + n2);
+        tw2 = __ldg(b.tw_col + 2 * N2 + n2);
+        tw4 = __ldg(b.tw_col + 4 * N2 + n2);
+        tw8 = __ldg(b.tw_col + 8 * N2 + n2);
+    }
 
     // finished rows of frame f leave the accumulator; the rest moves up by one hop
     auto emit_shift = [&](long long f) {
@@ -837,10 +859,7 @@ __global__ void __launch_bounds__(128, 4) col_inv_ola_kernel(const BandDev b, co
             float2 v[COL_R];
 #pragma unroll
             for (int k1 = 0; k1 < COL_R; k1++) v[k1] = B2[(long long)k1 * N2];
-#if !UPMIX_TW_IN_ROW
-#pragma unroll
-            for (int k1 = 1; k1 < COL_R; k1++) { const float2 t = __ldg(b.tw_col + k1 * N2 + n2); v[k1] = cmul(v[k1], make_float2(t.x, -t.y)); }
-#endif
+            if constexpr (!TWROW) apply_powers16<true>(v, tw1, tw2, tw4, tw8);
             Dft<COL_R, +1>::run(v);                          // v[n1] = (c_even[n], c_odd[n]), n = n1*N2 + n2
 #pragma unroll
             for (int n1 = 0; n1 < COL_R; n1++) {
@@ -853,10 +872,7 @@ __global__ void __launch_bounds__(128, 4) col_inv_ola_kernel(const BandDev b, co
             float2 v[COL_R];
 #pragma unroll
             for (int k1 = 0; k1 < COL_R; k1++) v[k1] = B1[((long long)half * COL_R + k1) * N2];
-#if !UPMIX_TW_IN_ROW
-#pragma unroll
-            for (int k1 = 1; k1 < COL_R; k1++) { const float2 t = __ldg(b.tw_col + k1 * N2 + n2); v[k1] = cmul(v[k1], make_float2(t.x, -t.y)); }
-#endif
+            if constexpr (!TWROW) apply_powers16<true>(v, tw1, tw2, tw4, tw8);
             Dft<COL_R, +1>::run(v);
 #pragma unroll
             for (int n1 = 0; n1 < COL_R; n1++) {
@@ -874,7 +890,8 @@ __global__ void __launch_bounds__(128, 4) col_inv_ola_kernel(const BandDev b, co
 // One thread per column: finish the inverse transform, window, add into the caller's overlap-add ring
 // [track][3][N] (frame-local order), emit the first hop and shift the ring by one hop.  A hop is 4 rows
 // of the thread's own column, so the in-place shift touches nobody else's samples.
-__global__ void __launch_bounds__(128, 4) col_inv_frame_kernel(const BandDev b, const WaveArgs w, float* __restrict__ ring,
+template <bool TWROW>
+__global__ void __launch_bounds__(128, TWROW ? 4 : 3) col_inv_frame_kernel(const BandDev b, const WaveArgs w, float* __restrict__ ring,
                                                                float* __restrict__ out_c, float* __restrict__ out_l,
                                                                float* __restrict__ out_r, long long out_stride) {
     const int N = b.n_fft;
@@ -893,14 +910,12 @@ __global__ void __launch_bounds__(128, 4) col_inv_frame_kernel(const BandDev b, 
     float2 vc[COL_R], v[COL_R];
 #pragma unroll
     for (int k1 = 0; k1 < COL_R; k1++) { vc[k1] = B2[(long long)k1 * N2]; v[k1] = B1[(long long)k1 * N2]; }
-#if !UPMIX_TW_IN_ROW
-#pragma unroll
-    for (int k1 = 1; k1 < COL_R; k1++) {
-        const float2 t = __ldg(b.tw_col + k1 * N2 + n2);
-        vc[k1] = cmul(vc[k1], make_float2(t.x, -t.y));
-        v[k1] = cmul(v[k1], make_float2(t.x, -t.y));
+    if constexpr (!TWROW) {
+        const float2 tw1 = __ldg(b.tw_col + N2 + n2), tw2 = __ldg(b.tw_col + 2 * N2 + n2), tw4 = __ldg(b.tw_col + 4 * N2 + n2),
+                     tw8 = __ldg(b.tw_col + 8 * N2 + n2);
+        apply_powers16<true>(vc, tw1, tw2, tw4, tw8);
+        apply_powers16<true>(v, tw1, tw2, tw4, tw8);
     }
-#endif
     Dft<COL_R, +1>::run(vc);
     Dft<COL_R, +1>::run(v);
 #pragma unroll
@@ -922,7 +937,8 @@ __global__ void __launch_bounds__(128, 4) col_inv_frame_kernel(const BandDev b, 
 cudaError_t launch_col_inv_frame(const BandDev& b, const WaveArgs& w, float* ring, float* out_c, float* out_l, float* out_r,
                                  long long out_stride, int n_tracks, cudaStream_t st) {
     const int n2 = b.n_fft / COL_R;
-    col_inv_frame_kernel<<<dim3((n2 + 127) / 128, 1, n_tracks), 128, 0, st>>>(b, w, ring, out_c, out_l, out_r, out_stride);
+    if (tw_in_row(b.n_fft)) col_inv_frame_kernel<true><<<dim3((n2 + 127) / 128, 1, n_tracks), 128, 0, st>>>(b, w, ring, out_c, out_l, out_r, out_stride);
+    else col_inv_frame_kernel<false><<<dim3((n2 + 127) / 128, 1, n_tracks), 128, 0, st>>>(b, w, ring, out_c, out_l, out_r, out_stride);
     return cudaGetLastError();
 }
 
@@ -1288,38 +1304,39 @@ int fused_smem_bytes(int n_fft) {
 
 cudaError_t launch_col_fwd(const BandDev& b, const SegArgs& a, const WaveArgs& w, int n_tracks, cudaStream_t st) {
     const int n2 = b.n_fft / COL_R;
-    col_fwd_kernel<<<dim3((n2 + 127) / 128, w.n_frames, n_tracks), 128, 0, st>>>(b, a, w);
+    if (tw_in_row(b.n_fft)) col_fwd_kernel<true><<<dim3((n2 + 127) / 128, w.n_frames, n_tracks), 128, 0, st>>>(b, a, w);
+    else col_fwd_kernel<false><<<dim3((n2 + 127) / 128, w.n_frames, n_tracks), 128, 0, st>>>(b, a, w);
     g_launches++;
     return cudaGetLastError();
 }
 
-template <int N2>
+template <int N2, bool TWROW>
 static cudaError_t launch_row_full(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
     static bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(row_mask_kernel<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(row_mask_kernel<N2, TWROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              RowCfg<N2>::SMEM);
         if (e != cudaSuccess) return e;
         attr_done[dev & 63] = true;
     }
-    row_mask_kernel<N2><<<dim3(COL_R / 2, w.n_frames / 2, n_tracks), RowCfg<N2>::T, RowCfg<N2>::SMEM, st>>>(b, w);
+    row_mask_kernel<N2, TWROW><<<dim3(COL_R / 2, w.n_frames / 2, n_tracks), RowCfg<N2>::T, RowCfg<N2>::SMEM, st>>>(b, w);
     g_launches++;
     return cudaGetLastError();
 }
-template <int N2>
+template <int N2, bool TWROW>
 static cudaError_t launch_row_pruned(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
     constexpr int SMEM = (PADSZ<RowCfg<N2>::PLAN>() + 12 * ROW_K) * (int)sizeof(float2);
     static bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(row_mask_pruned_kernel<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(row_mask_pruned_kernel<N2, TWROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
         attr_done[dev & 63] = true;
     }
-    row_mask_pruned_kernel<N2><<<dim3(COL_R / 2, w.n_frames / 2, n_tracks), N2 / 16, SMEM, st>>>(b, w);
+    row_mask_pruned_kernel<N2, TWROW><<<dim3(COL_R / 2, w.n_frames / 2, n_tracks), N2 / 16, SMEM, st>>>(b, w);
     g_launches++;
     return cudaGetLastError();
 }
@@ -1327,8 +1344,10 @@ static cudaError_t launch_row_pruned(const BandDev& b, const WaveArgs& w, int n_
 template <int N2>
 static cudaError_t launch_row_n(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
     static const bool allow = [] { const char* e = getenv("UPMIX_ROW_PRUNE"); return !(e && atoi(e) == 0); }();
-    if (allow && b.max_bin < COL_R * ROW_K) return launch_row_pruned<N2>(b, w, n_tracks, st);
-    return launch_row_full<N2>(b, w, n_tracks, st);
+    const bool twrow = tw_in_row(b.n_fft);
+    if (allow && b.max_bin < COL_R * ROW_K)
+        return twrow ? launch_row_pruned<N2, true>(b, w, n_tracks, st) : launch_row_pruned<N2, false>(b, w, n_tracks, st);
+    return twrow ? launch_row_full<N2, true>(b, w, n_tracks, st) : launch_row_full<N2, false>(b, w, n_tracks, st);
 }
 
 cudaError_t launch_row_mask(const BandDev& b, const WaveArgs& w, int n_tracks, cudaStream_t st) {
@@ -1343,7 +1362,8 @@ cudaError_t launch_row_mask(const BandDev& b, const WaveArgs& w, int n_tracks, c
 cudaError_t launch_col_inv_ola(const BandDev& b, const SegArgs& a, const WaveArgs& w, int n_runs, int n_tracks,
                                cudaStream_t st) {
     const int n2 = b.n_fft / COL_R;
-    col_inv_ola_kernel<<<dim3((n2 + 127) / 128, n_runs, n_tracks), 128, 0, st>>>(b, a, w);
+    if (tw_in_row(b.n_fft)) col_inv_ola_kernel<true><<<dim3((n2 + 127) / 128, n_runs, n_tracks), 128, 0, st>>>(b, a, w);
+    else col_inv_ola_kernel<false><<<dim3((n2 + 127) / 128, n_runs, n_tracks), 128, 0, st>>>(b, a, w);
     g_launches++;
     return cudaGetLastError();
 }
