@@ -416,7 +416,8 @@ __device__ __forceinline__ void fft_rows_fwd_pruned(float2* buf, int tid, const 
                 const int row = ROWS == 1 ? 0 : jj / NB, j = jj - row * NB, k = j & (NS - 1);
                 const float2* __restrict__ twp = tw + fft_tw_offset(PLAN, 1) + k;
 #pragma unroll
-                for (int r = 1; r < R; r++) w[it][r] = __ldg(twp + (r - 1) * NS);
+                for (int r = 1; r < R; r++)
+                    if (!UPMIX_TW_RECUR || (r & (r - 1)) == 0) w[it][r] = __ldg(twp + (r - 1) * NS);
                 const float2* __restrict__ src = buf + row * RS + PAD<PLAN>(j);
 #pragma unroll
                 for (int r = 0; r < R; r++) v[it][r] = src[r * LD_STR];
@@ -429,7 +430,14 @@ __device__ __forceinline__ void fft_rows_fwd_pruned(float2* buf, int tid, const 
             if (TOTAL % T == 0 || jj < TOTAL) {
                 const int row = ROWS == 1 ? 0 : jj / NB, j = jj - row * NB, k = j & (NS - 1);
 #pragma unroll
-                for (int r = 1; r < R; r++) v[it][r] = cmul(v[it][r], w[it][r]);
+                for (int r = 1; r < R; r++) {
+                    if (UPMIX_TW_RECUR && (r & (r - 1)) != 0) {      // as in stockham_pass: derived, not loaded
+                        int hb = 1;
+                        while (hb * 2 <= r) hb *= 2;
+                        w[it][r] = cmul(w[it][r - hb], w[it][hb]);
+                    }
+                    v[it][r] = cmul(v[it][r], w[it][r]);
+                }
                 Dft<R, -1>::run(v[it]);
                 float2* __restrict__ dst = buf + row * RS + PAD<PLAN>((j - k) * R + k);
 #pragma unroll

@@ -689,11 +689,14 @@ __global__ void __launch_bounds__(RowCfg<N2>::T) row_mask_kernel(const BandDev b
 // With the six rows no longer resident the CTA needs one row of shared memory, so it transforms one row
 // at a time with half the threads and two (or more) CTAs share an SM: one computes while the other
 // waits for its rows to arrive from HBM.
+// Register budget per thread: 65536 / (T * REGS) CTAs share an SM.  Without the four-step twiddles the kernel
+// fits 80 registers and a third CTA per SM pays (ms per band-hour, 128 / 100 / 85: 65536 6.16 / 6.15 / 5.78,
+// 32768 6.24 / 6.02 / 5.93); with them (16384 points) 128 is best (6.58 / 6.54 / 6.80).
 #ifndef UPMIX_ROWP_REGS
-#define UPMIX_ROWP_REGS 128       // register budget per thread: 65536 / (T * REGS) CTAs share an SM
+#define UPMIX_ROWP_REGS(TWROW) ((TWROW) ? 128 : 85)
 #endif
 template <int N2, bool TWROW>
-__global__ void __launch_bounds__(N2 / 16, 65536 / (N2 / 16 * UPMIX_ROWP_REGS)) row_mask_pruned_kernel(const BandDev b, const WaveArgs w) {
+__global__ void __launch_bounds__(N2 / 16, 65536 / (N2 / 16 * UPMIX_ROWP_REGS(TWROW))) row_mask_pruned_kernel(const BandDev b, const WaveArgs w) {
     constexpr int T = N2 / 16;
     constexpr int PL = RowCfg<N2>::PLAN;
     constexpr int RS = PADSZ<PL>();
