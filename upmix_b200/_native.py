@@ -340,7 +340,15 @@ class Plan:
         else:
             seg = int(segment_seconds * sample_rate)
         seg = max(align, -(-seg // align) * align)
-        bounds = list(range(0, n, seg)) + [n]
+        # the first segments are short and double up to `seg`: the device-to-host copy -- the longest stage
+        # of the pipeline -- starts after a few hundred microseconds instead of after two full chunks
+        bounds, pos, step = [0], 0, seg
+        if segment_seconds <= 0:
+            step = max(align, -(-int(8.0 * sample_rate) // align) * align)
+        while pos < n:
+            pos = min(n, pos + step)
+            bounds.append(pos)
+            step = min(seg, 2 * step)
         # input chunks: chunk i carries samples [bounds[i], bounds[i+1]); segment i needs chunks up to
         # the one holding sample min(n, bounds[i+1] + halo) - 1
         s_up.wait_stream(main)
@@ -353,7 +361,7 @@ class Plan:
                 ev = torch.cuda.Event()
                 ev.record(s_up)
             up_done.append(ev)
-        wsb = self.workspace_bytes(seg, 1)
+        wsb = self.workspace_bytes(max([b - a for a, b in zip(bounds[:-1], bounds[1:])] or [1]), 1)
         ws = self._workspace(wsb)
         import bisect
         for i, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
