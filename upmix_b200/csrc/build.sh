@@ -3,9 +3,15 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
-$NVCC $FLAGS -c upmix_kernels.cu -o upmix_kernels.o &
-$NVCC $FLAGS -c upmix_capi.cu -o upmix_capi.o &
-wait
-$NVCC $FLAGS -shared -o libupmix_b200.so upmix_kernels.o upmix_capi.o
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $UPMIX_EXTRA_FLAGS"
+SRCS="upmix_kernels upmix_capi upmix_fused_64_512 upmix_fused_1024_2048 upmix_fused_4096 upmix_fused_8192"
+pids=""
+for s in $SRCS; do
+    $NVCC $FLAGS -c $s.cu -o $s.o &
+    pids="$pids $!"
+done
+for p in $pids; do wait $p; done
+OBJS=""
+for s in $SRCS; do OBJS="$OBJS $s.o"; done
+$NVCC $FLAGS -shared -o libupmix_b200.so $OBJS
 echo "built $(pwd)/libupmix_b200.so"

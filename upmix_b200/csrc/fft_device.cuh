@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #ifndef UPMIX_TW_RECUR
 #define UPMIX_TW_RECUR 1          // derive the non-power-of-two pass twiddles instead of loading them
 #endif
@@ -189,9 +191,25 @@ __host__ __device__ constexpr int PADSZ() { return fft_size(PLAN) + (fft_size(PL
 struct NoAux {};
 template <class Pre, class Put>
 struct StoreFn {
+    static constexpr bool WITH_R = false;
     Pre pre;
     Put put;
 };
+// Variant whose functors also receive r, the output's index within its butterfly: pre(row, k, r), put(row, k,
+// value, aux, r).  r is a literal after unrolling, so a store functor can specialise per output at compile time
+// (the overlap-add treats the four hops of a frame differently).
+template <class Pre, class Put>
+struct StoreFnR {
+    static constexpr bool WITH_R = true;
+    Pre pre;
+    Put put;
+};
+template <class Pre, class Put>
+__device__ __forceinline__ StoreFnR<Pre, Put> make_store_r(Pre pre, Put put) { return StoreFnR<Pre, Put>{pre, put}; }
+template <class St, bool R = St::WITH_R>
+struct AuxOf { using type = decltype(std::declval<St&>().pre(0, 0)); };
+template <class St>
+struct AuxOf<St, true> { using type = decltype(std::declval<St&>().pre(0, 0, 0)); };
 template <class Pre, class Put>
 __device__ __forceinline__ StoreFn<Pre, Put> make_store(Pre pre, Put put) { return StoreFn<Pre, Put>{pre, put}; }
 template <class Put>
@@ -225,7 +243,7 @@ __device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2
     constexpr int ST_STR = NS == 1 ? 1 : NS + NS / PERIOD;
     float2 v[IT][R];
     float2 w[IT][NS > 1 ? R : 1];
-    decltype(st.pre(0, 0)) aux[IT][LAST ? R : 1];
+    typename AuxOf<St>::type aux[IT][LAST ? R : 1];
 #pragma unroll
     for (int it = 0; it < IT; it++) {
         const int jj = tid + it * T;
@@ -242,7 +260,10 @@ __device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2
             if (LAST) {
                 const int j0 = (j - k) * R + k;
 #pragma unroll
-                for (int r = 0; r < R; r++) aux[it][r] = st.pre(row, j0 + r * NS);
+                for (int r = 0; r < R; r++) {
+                    if constexpr (St::WITH_R) aux[it][r] = st.pre(row, j0 + r * NS, r);
+                    else aux[it][r] = st.pre(row, j0 + r * NS);
+                }
             }
             const float2* __restrict__ src = buf + row * RS + PAD<PLAN>(j);
 #pragma unroll
@@ -282,7 +303,10 @@ __device__ __forceinline__ void stockham_pass(float2* buf, int tid, const float2
             float2* __restrict__ dst = buf + row * RS + PAD<PLAN>(j0);
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                if (LAST) st.put(row, j0 + r * NS, v[it][r], aux[it][r]);
+                if (LAST) {
+                    if constexpr (St::WITH_R) st.put(row, j0 + r * NS, v[it][r], aux[it][r], r);
+                    else st.put(row, j0 + r * NS, v[it][r], aux[it][r]);
+                }
                 else if (ST_LIN) dst[r * ST_STR] = v[it][r];
                 else buf[row * RS + PAD<PLAN>(j0 + r * NS)] = v[it][r];
             }
