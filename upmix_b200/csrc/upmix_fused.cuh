@@ -65,7 +65,7 @@ UPMIX_FUSED_CFG_X(64, UPMIX_CFG_64)
 #endif
 UPMIX_FUSED_CFG_X(128, UPMIX_CFG_128)
 #ifndef UPMIX_CFG_256
-#define UPMIX_CFG_256 mkplan(8, 8, 4), mkplan(4, 8, 8), mkplan(2, 8, 8), 32, 12
+#define UPMIX_CFG_256 mkplan(8, 8, 4), mkplan(4, 8, 8), mkplan(8, 4, 4), 32, 12
 #endif
 UPMIX_FUSED_CFG_X(256, UPMIX_CFG_256)
 #ifndef UPMIX_CFG_512
@@ -100,6 +100,9 @@ enum { MODE_PLAIN = 0, MODE_FOLD = 1, MODE_MERGED = 2 };
 // ring traffic: the ring and the copy-out were 15-18 % of the kernel's shared-memory wavefronts.
 #ifndef UPMIX_DIRECT_EMIT
 #define UPMIX_DIRECT_EMIT 1
+#endif
+#ifndef UPMIX_FE_MIN_N
+#define UPMIX_FE_MIN_N 256        // smallest size that uses it (measured; see launch_fused_nm)
 #endif
 template <int N, int MODE, bool FE>
 __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXREG) band_fused_kernel(const BandDev b, const SegArgs a) {
@@ -614,8 +617,9 @@ template <int N, int MODE>
 static cudaError_t launch_fused_nm(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st) {
     static const bool allow = [] { const char* e = getenv("UPMIX_DIRECT_EMIT"); return UPMIX_DIRECT_EMIT && !(e && atoi(e) == 0); }();
     // measured, ms per band-hour without / with: 8192 6.22 / 5.75, 4096 5.66 / 5.33, 2048 5.59 / 5.39, 1024 5.09 / 4.87,
-    // 512 5.15 / 5.07, 256 5.91 / 6.27 (spills on its 168-register budget): from 512 points up
-    if (allow && N >= 512 && b.hop * 4 == b.n_fft && !a.mix) return launch_fused_nmf<N, MODE, true>(b, a, n_runs, n_tracks, st);
+    // 512 5.15 / 5.07, 256 5.91 / 6.27 with the half-size first pass fused (spills), 5.79 / 5.49 with the half transform
+    // on its own ({8,4,4}): from 256 points up
+    if (allow && N >= UPMIX_FE_MIN_N && b.hop * 4 == b.n_fft && !a.mix) return launch_fused_nmf<N, MODE, true>(b, a, n_runs, n_tracks, st);
     return launch_fused_nmf<N, MODE, false>(b, a, n_runs, n_tracks, st);
 }
 template <int N>

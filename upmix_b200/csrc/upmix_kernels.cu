@@ -1,8 +1,8 @@
 // Hand-written sm_100a kernels for the multi-band STFT centre-extraction path.
 //
 //   band_fused_kernel<N>    N <= 8192: whole per-band chain in one CTA per run of hops --
-//                           frame load + analysis window -> packed complex FFT (L + iR) in shared
-//                           memory -> Hermitian split, band gain, centre mask -> inverse FFT of
+//   (upmix_fused.cuh,       frame load + analysis window -> packed complex FFT (L + iR) in shared
+//    upmix_fused_*.cu)      memory -> Hermitian split, band gain, centre mask -> inverse FFT of
 //                           Ls + i*Rs (N points) and of C (N/2 points, real-signal packing) ->
 //                           synthesis window -> overlap-add ring in shared memory -> finished hops.
 //   col_fwd_kernel          N >= 16384 (four-step, N = 16 x N2): radix-16 column DFT of the windowed
