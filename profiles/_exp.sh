@@ -1,1 +1,1 @@
-for v in cur fe256a fe256b c256c; do echo $v; if [ $v = cur ]; then unset UPMIX_B200_LIB; else export UPMIX_B200_LIB=$PWD/gpurun_variants/lib_$v.so; fi; python -m pytest tests -m gpu -x -q -k "every_size" 2>&1 | tail -1; python profiles/band_bench.py 3600 256:d 256; done
+for v in cur m512a m512b; do echo $v; if [ $v = cur ]; then unset UPMIX_B200_LIB; else export UPMIX_B200_LIB=$PWD/gpurun_variants/lib_$v.so; fi; python profiles/band_bench.py 3600 512:d 512; done
