@@ -577,3 +577,35 @@ def test_fir_filter_vs_reference_fixture(ce, golden_dir):
         from scipy.signal import lfilter
         ref = lfilter(g["ref_hp_short"].astype(np.float64), 1.0, x.astype(np.float64))
         assert float(np.max(np.abs(ref - y.cpu().numpy()))) <= 1e-6
+
+
+def test_fused_emit_is_bit_identical_to_ring_copy_out(ce, tmp_path):
+    """The fused-emit kernels (finished hops leave from the last inverse passes) and the ring + copy-out kernels
+    do the same float32 additions in the same order: bit-identical outputs.  The switch is read once per
+    process, so the two variants run in subprocesses."""
+    import subprocess
+    import sys
+    script = tmp_path / "run.py"
+    script.write_text(
+        "import sys, contextlib, io, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import upmix_b200.center_extraction as ce\n"
+        "from oracle import upmix_oracle as uo\n"
+        "sr = 48000\n"
+        "outs = []\n"
+        "for edges, mb in (([0, 200, 2000], 8192), ([0, 500, 2000, 8000], 4096), ([0, 3000, 9000], 512)):\n"
+        "    with contextlib.redirect_stdout(io.StringIO()):\n"
+        "        ext = ce.chain_bands(edges, 0.75, ce.make_blackman_harris, sr, 'raised_cosine', max_block_size=mb)\n"
+        "    L, R = uo.synth_stereo(2 * sr + 333, 5, stress=True)\n"
+        "    outs += list(ce.extract_center_left_right_multi_band_in_memory(L, R, sr, ext))\n"
+        "    outs += list(ce.extract_stereo_fold_down(L, R, sr, ext))\n"
+        "np.savez(sys.argv[1], *outs)\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = {}
+    for flag in ("0", "1"):
+        out = tmp_path / f"out{flag}.npz"
+        env = dict(os.environ, UPMIX_DIRECT_EMIT=flag, UPMIX_DIRECT_MIN="1")
+        subprocess.run([sys.executable, str(script), str(out)], check=True, env=env)
+        res[flag] = np.load(out)
+    assert len(res["0"].files) == len(res["1"].files) > 0
+    for k in res["0"].files:
+        assert np.array_equal(res["0"][k], res["1"][k]), k
