@@ -313,7 +313,10 @@ __global__ void __launch_bounds__(N2 / 16, 65536 / (N2 / 16 * UPMIX_ROWP_REGS(TW
 // the 16-row accumulator by 4 rows (hop = N/4 = 4*N2), the 4 rows that fall out are finished samples.
 // TWROW = false: the kernel also applies the four-step twiddles, which costs registers: 3 CTAs per SM (168
 // registers, no spills) instead of 4 (measured: 65536 6.70 -> 6.14 ms per band-hour)
-template <bool TWROW>
+// ACCUM: the band adds its hops to what the outputs hold (a compile-time variant: the values it prefetches cost
+// 12 registers, which the storing variant should not pay for; it keeps the occupancy of its twin -- measured on
+// the default six bands, 1-hour track: 4 CTAs per SM with 72 B of spills 29.6 ms, 3 CTAs per SM without 30.8 ms).
+template <bool TWROW, bool ACCUM>
 __global__ void __launch_bounds__(128, TWROW ? 4 : 3) col_inv_ola_kernel(const BandDev b, const SegArgs a, const WaveArgs w) {
     const int N2 = b.n_fft / COL_R;
     const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -343,6 +346,22 @@ __global__ void __launch_bounds__(128, TWROW ? 4 : 3) col_inv_ola_kernel(const B
     }
 
     // finished rows of frame f leave the accumulator; the rest moves up by one hop
+    // accum: what the output already holds for the hop frame f finishes (the bands before this one) is requested
+    // together with the frame's scratch rows and waits in registers -- loaded at the store, one dependent HBM
+    // round trip per sample made this kernel 2.7x slower than its storing twin
+    float pv[3][ACCUM ? COL_R / 4 : 1];
+    auto request_prev = [&](long long f) {
+        if (!ACCUM || f < h0 || f >= h1) return;
+        const long long s0 = f * H + n2;
+#pragma unroll
+        for (int n1 = 0; n1 < COL_R / 4; n1++) {
+            const long long s = s0 + n1 * N2;
+            const bool in = s >= a.seg_begin && s < a.seg_end;
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++)
+                if (ch > 0 || !a.mix) pv[ch][ACCUM ? n1 : 0] = in ? __ldcs(outp[ch] + (s - a.out_begin)) : 0.f;
+        }
+    };
     auto emit_shift = [&](long long f) {
         const bool emit = f >= h0 && f < h1;
         const long long s0 = f * H + n2;
@@ -354,11 +373,11 @@ __global__ void __launch_bounds__(128, TWROW ? 4 : 3) col_inv_ola_kernel(const B
                 if (a.mix) {                     // fold-down epilogue: Ls + 0.5 C, Rs + 0.5 C
                     const float hc = 0.5f * acc[0][n1];
                     const float vl = acc[1][n1] + hc, vr = acc[2][n1] + hc;
-                    outp[1][o] = a.accum ? outp[1][o] + vl : vl;
-                    outp[2][o] = a.accum ? outp[2][o] + vr : vr;
+                    __stcs(outp[1] + o, ACCUM ? pv[1][ACCUM ? n1 : 0] + vl : vl);
+                    __stcs(outp[2] + o, ACCUM ? pv[2][ACCUM ? n1 : 0] + vr : vr);
                 } else {
 #pragma unroll
-                    for (int ch = 0; ch < 3; ch++) outp[ch][o] = a.accum ? outp[ch][o] + acc[ch][n1] : acc[ch][n1];
+                    for (int ch = 0; ch < 3; ch++) __stcs(outp[ch] + o, ACCUM ? pv[ch][ACCUM ? n1 : 0] + acc[ch][n1] : acc[ch][n1]);
                 }
             }
         }
@@ -394,6 +413,7 @@ __global__ void __launch_bounds__(128, TWROW ? 4 : 3) col_inv_ola_kernel(const B
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             float2 v[COL_R];
+            request_prev(2 * p + half);
 #pragma unroll
             for (int k1 = 0; k1 < COL_R; k1++) v[k1] = B1[((long long)half * COL_R + k1) * N2];
             if constexpr (!TWROW) apply_powers16<true>(v, tw1, tw2, tw4, tw8);
@@ -864,8 +884,14 @@ cudaError_t launch_row_mask(const BandDev& b, const WaveArgs& w, int n_tracks, c
 cudaError_t launch_col_inv_ola(const BandDev& b, const SegArgs& a, const WaveArgs& w, int n_runs, int n_tracks,
                                cudaStream_t st) {
     const int n2 = b.n_fft / COL_R;
-    if (tw_in_row(b.n_fft)) col_inv_ola_kernel<true><<<dim3((n2 + 127) / 128, n_runs, n_tracks), 128, 0, st>>>(b, a, w);
-    else col_inv_ola_kernel<false><<<dim3((n2 + 127) / 128, n_runs, n_tracks), 128, 0, st>>>(b, a, w);
+    const dim3 grid((n2 + 127) / 128, n_runs, n_tracks);
+    if (tw_in_row(b.n_fft)) {
+        if (a.accum) col_inv_ola_kernel<true, true><<<grid, 128, 0, st>>>(b, a, w);
+        else col_inv_ola_kernel<true, false><<<grid, 128, 0, st>>>(b, a, w);
+    } else {
+        if (a.accum) col_inv_ola_kernel<false, true><<<grid, 128, 0, st>>>(b, a, w);
+        else col_inv_ola_kernel<false, false><<<grid, 128, 0, st>>>(b, a, w);
+    }
     g_launches++;
     return cudaGetLastError();
 }
