@@ -189,7 +189,9 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
             a.out_l = out_l;
             a.out_r = out_r;
             a.out_stride = out_stride;
-            a.accum = first ? 0 : 1;
+            // UPMIX_FORCE_ACCUM=1 (measurement only): the first pipeline accumulates too, onto whatever the outputs hold
+            static const bool force_accum = [] { const char* e = getenv("UPMIX_FORCE_ACCUM"); return e && atoi(e) != 0; }();
+            a.accum = first && !force_accum ? 0 : 1;
             a.mix = p->out_mode == UPMIX_OUT_FOLD && !p->fold_in_freq ? 1 : 0;
             first = false;
         } else {
