@@ -697,17 +697,7 @@ __device__ __forceinline__ void mega_phase(float2* Z, float2* Cz, int tid, const
             g[RL] = 0.f;
 #pragma unroll
             for (int r = 0; r < RH; r++) wp[r] = __ldg(twp + j1 + r * NSL);
-        } else {
-#pragma unroll
-            for (int r = 0; r <= RH; r++) {              // butterfly 0: bins r NSL <-> (RL-r) NSL
-                gk[r] = r * NSL;
-                g[r] = __ldg(gain + gk[r]);
-            }
-#pragma unroll
-            for (int r = 0; r < RH; r++) {               // butterfly NSL/2: bins NSL/2 + r NSL <-> NSL/2 + (RL-1-r) NSL
-                gk[RH + 1 + r] = NSL / 2 + r * NSL;
-                g[RH + 1 + r] = __ldg(gain + gk[RH + 1 + r]);
-            }
+        } else {                                         // (its pairs' gains are loaded by the lanes that mask them)
 #pragma unroll
             for (int r = 0; r < RH; r++)                 // k = (r+1) NSL for r < RL/4 (k = 0 needs none);  then k = NSL/2 + r' NSL
                 wp[r] = __ldg(twp + (r < RL / 4 ? (r + 1) * NSL : NSL / 2 + (r - RL / 4) * NSL));
@@ -804,32 +794,66 @@ __device__ __forceinline__ void mega_phase(float2* Z, float2* Cz, int tid, const
                 }
             }
         }
-    } else {
-        float2 c1[RH + 1], c2[RH];
-        {
-            float2 t = v1[0];
-            mask2(v1[0], t, 0, c1[0]);                   // bin 0 is its own mirror
-            t = v1[RH];
-            mask2(v1[RH], t, RH, c1[RH]);                // so is bin N/2
-        }
+    }
+    // Thread 0's two self-mirrored butterflies hold 2 RL + 1 mirror pairs of their own.  Masked by that one
+    // thread they would cost its warp a second mask round of full length, and the CTA a wait at the next barrier
+    // (4 % of the 8192-point kernel); instead the first lanes of warp 0 take one pair each: thread 0 parks its 2 RL
+    // values in a small shared scratch, lanes 0 .. RL mask one pair apiece, thread 0 collects the results.
+    __shared__ float2 sp[2 * RL], sc[RL + 1];
+    if (tid < 32) {                                      // warp 0
+        if (special) {
 #pragma unroll
-        for (int r = 1; r < RH; r++) mask2(v1[r], v1[RL - r], r, c1[r]);
-#pragma unroll
-        for (int r = 0; r < RH; r++) mask2(v2[r], v2[RL - 1 - r], RH + 1 + r, c2[r]);
-        if (!fold) {
-#pragma unroll
-            for (int r = 0; r <= RL / 4; r++) {          // k = r NSL, M - k = (RH - r) NSL
-                float2 zk, zmk;
-                pack_pair(c1[r], c1[RH - r], r == 0 ? make_float2(1.f, 0.f) : wp[r - 1], zk, zmk);
-                put_a(r, zk);
-                if (r > 0) put_a(RH - r, zmk);
+            for (int r = 0; r < RL; r++) {
+                sp[r] = v1[r];
+                sp[RL + r] = v2[r];
             }
+        }
+        __syncwarp();
+        if (tid <= RL) {
+            // pair p: p <= RH: bins p NSL <-> (RL - p) NSL of butterfly 0 (p = 0 and p = RH are their own mirrors);
+            //         p > RH:  bins NSL/2 + r NSL <-> NSL/2 + (RL-1-r) NSL of butterfly NSL/2, r = p - RH - 1
+            const int p = tid;
+            const int r = p - RH - 1;
+            const int ia = p <= RH ? p : RL + r;
+            const int ib = p <= RH ? (RL - p) & (RL - 1) : 2 * RL - 1 - r;
+            const int bin = p <= RH ? p * NSL : NSL / 2 + r * NSL;
+            const float gp = __ldg(gain + bin);
+            const float2 a = sp[ia], bb = sp[ib];
+            float2 ylo, yhi, c;
+            if constexpr (MERGED) mask_bin_merged(a, bb, gp, gain + bin, n_gains, gain_stride, ylo, yhi, c);
+            else mask_bin(a, bb, gp, ylo, yhi, c);
+            if (fold) {
+                const float2 u = cadd(make_float2(c.x, c.x), make_float2(-c.y, c.y));
+                ylo = caxpy(u, 0.5f, ylo);
+                yhi = caxpy(make_float2(u.y, u.x), 0.5f, yhi);
+            }
+            __syncwarp((2u << RL) - 1u);                 // every pair read before any is overwritten
+            sp[ia] = ylo;
+            if (ib != ia) sp[ib] = yhi;
+            sc[p] = c;
+        }
+        __syncwarp();
+        if (special) {
 #pragma unroll
-            for (int r = 0; r < RL / 4; r++) {           // k = NSL/2 + r NSL, M - k = NSL/2 + (RH-1-r) NSL
-                float2 zk, zmk;
-                pack_pair(c2[r], c2[RH - 1 - r], wp[RL / 4 + r], zk, zmk);
-                put_b(r, zk);
-                put_b(RH - 1 - r, zmk);
+            for (int r = 0; r < RL; r++) {
+                v1[r] = sp[r];
+                v2[r] = sp[RL + r];
+            }
+            if (!fold) {
+#pragma unroll
+                for (int r = 0; r <= RL / 4; r++) {      // k = r NSL, M - k = (RH - r) NSL
+                    float2 zk, zmk;
+                    pack_pair(sc[r], sc[RH - r], r == 0 ? make_float2(1.f, 0.f) : wp[r - 1], zk, zmk);
+                    put_a(r, zk);
+                    if (r > 0) put_a(RH - r, zmk);
+                }
+#pragma unroll
+                for (int r = 0; r < RL / 4; r++) {       // k = NSL/2 + r NSL, M - k = NSL/2 + (RH-1-r) NSL
+                    float2 zk, zmk;
+                    pack_pair(sc[RH + 1 + r], sc[RH + 1 + RH - 1 - r], wp[RL / 4 + r], zk, zmk);
+                    put_b(r, zk);
+                    put_b(RH - 1 - r, zmk);
+                }
             }
         }
     }
