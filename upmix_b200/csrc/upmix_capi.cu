@@ -53,11 +53,13 @@ struct DeviceGuard {
     }
 };
 
-int k3_hops_per_run() {
-    static const int v = [] { const char* e = getenv("UPMIX_K3_RUN"); return e ? std::max(4, atoi(e)) : 32; }();
-    return v;
+// Hops a column thread of col_inv_ola finishes in one run (plus 3 warm-up frames): long runs amortise the
+// warm-up, short ones keep the grid full when a wave is short (time shards of the host pipeline, short tracks).
+int k3_hops_per_run(int64_t wave_hops) {
+    static const int forced = [] { const char* e = getenv("UPMIX_K3_RUN"); return e ? std::max(4, atoi(e)) : 0; }();
+    if (forced) return forced;
+    return wave_hops >= 4096 ? 64 : wave_hops >= 256 ? 32 : 16;
 }
-#define K3_HOPS_PER_RUN k3_hops_per_run()
 
 }  // namespace
 
@@ -88,6 +90,7 @@ namespace {
 struct Layout {
     int64_t ws_seg = 0;         // per-track stride of a band output in the workspace (floats)
     int64_t band_out_bytes = 0;
+    int k3_run = 32;            // large path: hops per column-thread run of col_inv_ola
     int wave_hops = 0;          // large path: hops finished per wave
     int wave_frames = 0;        // large path: frames resident per wave (even)
     int64_t a_bytes = 0, b1_bytes = 0, b2_bytes = 0;
@@ -118,10 +121,15 @@ Layout make_layout(const UpmixPlan* p, int64_t seg_len, int n_tracks, bool stage
         for (const BandDev& b : p->bands)
             if (b.n_fft > FUSED_MAX_N) hop_min = std::min<int64_t>(hop_min, b.hop);
         const int64_t seg_hops = (seg_len + hop_min - 1) / hop_min + 1;
-        int64_t wave_total = 2048;     // hops per wave over all tracks (tuning knob: UPMIX_WAVE_HOPS)
+        // hops per wave over all tracks (tuning knob: UPMIX_WAVE_HOPS).  Measured with the final kernels, ms per
+        // band-hour for waves of 1024 / 2048 / 4096 / 8192 hops (runs of 64 hops per column thread): 65536 points
+        // 6.65 / 6.02 / 5.65 / 5.61, 16384 points 9.69 / 7.29 / 6.26 / 6.14; the scratch of a 65536-point band is
+        // 1.3 MB per hop (10.7 GB for 8192 hops, of 180 GB)
+        int64_t wave_total = 8192;
         if (const char* ev = getenv("UPMIX_WAVE_HOPS")) wave_total = std::max(16, atoi(ev));
         int64_t wh = std::max<int64_t>(16, wave_total / std::max(1, n_tracks));
-        wh = round_up(std::min<int64_t>(wh, round_up(seg_hops, K3_HOPS_PER_RUN)), K3_HOPS_PER_RUN);
+        l.k3_run = k3_hops_per_run(std::min<int64_t>(wh, seg_hops));
+        wh = round_up(std::min<int64_t>(wh, round_up(seg_hops, l.k3_run)), l.k3_run);
         l.wave_hops = (int)wh;
         l.wave_frames = (int)wh + 6;
         const int64_t per_frame = (int64_t)p->max_large_n * (int64_t)sizeof(float2);
@@ -133,12 +141,20 @@ Layout make_layout(const UpmixPlan* p, int64_t seg_len, int n_tracks, bool stage
     return l;
 }
 
-// Hops per CTA of the fused kernel: long runs amortise the (n_fft/hop - 1) warm-up frames, but the
-// grid should fill every SM with a few waves of co-resident CTAs.
+// Hops per CTA of the fused kernel.  A run replays the (n_fft/hop - 1) frames before it, so long runs are
+// cheaper; but the grid should come out as a whole number of waves of co-resident CTAs, or the last wave leaves
+// SMs idle (measured, 8192 points, 1-hour track, run = 64 / 96 / 128 / 192 hops: 5.81 / 5.74 / 6.24 / 5.63 ms).
+// The smallest number of full waves whose runs stay within `run_max` hops is taken.
 int pick_hops_per_run(const UpmixPlan* p, int n_fft, int64_t total_hops, int n_tracks) {
-    const int64_t target_ctas = (int64_t)p->sm_count * fused_ctas_per_sm(n_fft) * 3;
-    int64_t r = (total_hops * n_tracks + target_ctas - 1) / target_ctas;
-    return (int)std::min<int64_t>(64, std::max<int64_t>(8, r));
+    static const int run_max = [] { const char* e = getenv("UPMIX_RUN_MAX"); return e ? std::max(8, atoi(e)) : 192; }();
+    const int64_t slots = (int64_t)p->sm_count * fused_ctas_per_sm(n_fft);
+    const int64_t work = total_hops * n_tracks;
+    for (int64_t waves = 1;; waves++) {
+        // runs per track such that all tracks together fill `waves` waves
+        const int64_t runs_per_track = std::max<int64_t>(1, waves * slots / n_tracks);
+        const int64_t r = (total_hops + runs_per_track - 1) / runs_per_track;
+        if (r <= run_max || waves * slots >= work) return (int)std::max<int64_t>(8, r);
+    }
 }
 
 // Runs every band of the plan over output samples [seg_begin, seg_end) into the band workspace,
@@ -232,7 +248,7 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
             w.b1 = reinterpret_cast<float2*>(scratch + lay.a_bytes);
             w.b2 = reinterpret_cast<float2*>(scratch + lay.a_bytes + lay.b1_bytes);
             (void)per_frame;
-            a.hops_per_run = K3_HOPS_PER_RUN;
+            a.hops_per_run = lay.k3_run;
             const int64_t h_begin = a.hop_begin, h_end = a.hop_end;
             for (int64_t w0 = h_begin; w0 < h_end; w0 += lay.wave_hops) {
                 const int64_t w1 = std::min<int64_t>(w0 + lay.wave_hops, h_end);
@@ -244,7 +260,7 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
                 SegArgs aw = a;
                 aw.hop_begin = w0;
                 aw.hop_end = w1;
-                const int n_runs = (int)((w1 - w0 + K3_HOPS_PER_RUN - 1) / K3_HOPS_PER_RUN);
+                const int n_runs = (int)((w1 - w0 + lay.k3_run - 1) / lay.k3_run);
                 CU_CHECK(launch_col_fwd(b, aw, w, n_tracks, st));
                 CU_CHECK(launch_row_mask(b, w, n_tracks, st));
                 CU_CHECK(launch_col_inv_ola(b, aw, w, n_runs, n_tracks, st));
