@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
     const float2* __restrict__ twp = b.tw_pack;
 
     // Frame staging, two variants (FusedCfg<N>::TMA, chosen by measurement):
-    //  * TMA (N >= 2048): the raw samples of a frame land in the (then idle) transform buffer Z as two
+    //  * TMA (N >= 1024): the raw samples of a frame land in the (then idle) transform buffer Z as two
     //    planar arrays SL[N], SR[N]: one elected thread issues two bulk copies (cp.async.bulk + mbarrier)
     //    for the NEXT frame as soon as the inverse transform of Ls + i Rs has released Z, so the copy
     //    overlaps the centre's inverse transform and the copy-out; pass 0 of the next frame reads SL/SR
