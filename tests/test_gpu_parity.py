@@ -609,3 +609,73 @@ def test_fused_emit_is_bit_identical_to_ring_copy_out(ce, tmp_path):
     assert len(res["0"].files) == len(res["1"].files) > 0
     for k in res["0"].files:
         assert np.array_equal(res["0"][k], res["1"][k]), k
+
+
+def test_no_writes_outside_outputs_and_workspace(ce):
+    """compute-sanitizer is not available on the GPU pool, so the bounds are checked the plain way: outputs and
+    workspace sit between canary regions, and after runs that exercise every kernel family (fused sizes with
+    and without the fused middle, the four-step path, staged and direct band sums, track batches with strides,
+    a time shard) the canaries must be untouched."""
+    import ctypes
+    import torch
+    from upmix_b200 import _native
+    lib = _native.load_library()
+    sr = 48000
+    G = 4096                                       # canary elements on each side
+    canary = torch.tensor([0x7fc0dead], dtype=torch.int32).view(torch.float32).item()
+
+    def guarded(n_elems, dtype=torch.float32):
+        buf = torch.empty(n_elems + 2 * G, dtype=dtype, device="cuda")
+        if dtype == torch.float32:
+            buf.view(torch.int32).fill_(0x7fc0dead)
+        else:
+            buf.fill_(0xA5)
+        return buf
+
+    def intact(buf, n_elems, dtype=torch.float32):
+        if dtype == torch.float32:
+            v = buf.view(torch.int32)
+            return bool((v[:G] == 0x7fc0dead).all()) and bool((v[G + n_elems:] == 0x7fc0dead).all())
+        return bool((buf[:G] == 0xA5).all()) and bool((buf[G + n_elems:] == 0xA5).all())
+
+    cases = [([0, 30, 120, 480, 1920, 7680], 65536, 1, 3 * 65536 + 4321),      # default six bands: merged four-step, 16384, fused
+             ([0, 200, 2000], 8192, 3, 40000),                                  # fused middle sizes, track batch
+             ([0, 3000, 9000], 512, 2, 9999),                                   # small sizes
+             ([0, 1000], 65536, 1, 70001)]                                      # four-step band with gain beyond bin 512
+    for direct_min in ("1", str(1 << 60)):
+        os.environ["UPMIX_DIRECT_MIN"] = direct_min
+        try:
+            for edges, mb, tracks, n in cases:
+                ext = quiet(ce.chain_bands, edges, 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=mb)
+                plan = ce.plan_for(ext)
+                stride = n + 37                                                 # odd stride: scalar store paths
+                L = torch.randn(tracks * stride, device="cuda") * 0.1
+                R = torch.randn(tracks * stride, device="cuda") * 0.1
+                for a, b in ((0, n), (n // 3 + 5, 2 * n // 3 + 11)):            # whole track, then a shard
+                    outs = [guarded(tracks * stride) for _ in range(3)]
+                    wsb = plan.workspace_bytes(b - a, tracks)
+                    ws = guarded(wsb, torch.uint8)
+                    ws_ptr = ws.data_ptr() + G
+                    pad = (-ws_ptr) % 256                                      # the ABI wants a 256-byte aligned workspace
+                    assert pad <= G - 256
+                    rc = lib.upmix_process_segment(plan._h, L.data_ptr(), R.data_ptr(), 0, n, n, a, b, tracks, stride,
+                                                   *[o.data_ptr() + 4 * G for o in outs], stride, ws_ptr + pad, wsb - pad if wsb else 0, None)
+                    if rc == -4:                                               # alignment padding ate into a tight workspace: retry larger
+                        ws = guarded(wsb + 256, torch.uint8)
+                        ws_ptr = ws.data_ptr() + G
+                        pad = (-ws_ptr) % 256
+                        rc = lib.upmix_process_segment(plan._h, L.data_ptr(), R.data_ptr(), 0, n, n, a, b, tracks, stride,
+                                                       *[o.data_ptr() + 4 * G for o in outs], stride, ws_ptr + pad, wsb, None)
+                        wsb += 256
+                    assert rc == 0, lib.upmix_last_error()
+                    torch.cuda.synchronize()
+                    assert intact(ws, wsb, torch.uint8), ("workspace", edges, a, b, direct_min)
+                    for o in outs:
+                        assert intact(o, tracks * stride), ("output", edges, a, b, direct_min)
+                        body = o[G:G + tracks * stride].view(tracks, stride)
+                        # the gaps between tracks (stride - n elements) and, for a shard, everything past its length stay canaries
+                        assert bool((body[:, b - a:].view(torch.int32) == 0x7fc0dead).all()), ("gap", edges, a, b, direct_min)
+                        assert bool(torch.isfinite(body[:, :b - a]).all())
+        finally:
+            os.environ.pop("UPMIX_DIRECT_MIN", None)
+    assert canary != canary                        # the canary is a NaN: any arithmetic on it would have shown
