@@ -55,10 +55,11 @@ struct DeviceGuard {
 
 // Hops a column thread of col_inv_ola finishes in one run (plus 3 warm-up frames): long runs amortise the
 // warm-up, short ones keep the grid full when a wave is short (time shards of the host pipeline, short tracks).
-int k3_hops_per_run(int64_t wave_hops) {
+int k3_hops_per_run(int64_t wave_hops, int n_tracks) {
     static const int forced = [] { const char* e = getenv("UPMIX_K3_RUN"); return e ? std::max(4, atoi(e)) : 0; }();
     if (forced) return forced;
-    return wave_hops >= 4096 ? 64 : wave_hops >= 256 ? 32 : 16;
+    const int64_t parallel = wave_hops * n_tracks;      // hops of a wave over all tracks: what fills the grid
+    return parallel >= 4096 && wave_hops >= 128 ? 64 : parallel >= 256 ? 32 : 16;
 }
 
 }  // namespace
@@ -128,7 +129,7 @@ Layout make_layout(const UpmixPlan* p, int64_t seg_len, int n_tracks, bool stage
         int64_t wave_total = 8192;
         if (const char* ev = getenv("UPMIX_WAVE_HOPS")) wave_total = std::max(16, atoi(ev));
         int64_t wh = std::max<int64_t>(16, wave_total / std::max(1, n_tracks));
-        l.k3_run = k3_hops_per_run(std::min<int64_t>(wh, seg_hops));
+        l.k3_run = k3_hops_per_run(std::min<int64_t>(wh, seg_hops), n_tracks);
         wh = round_up(std::min<int64_t>(wh, round_up(seg_hops, l.k3_run)), l.k3_run);
         l.wave_hops = (int)wh;
         l.wave_frames = (int)wh + 6;
