@@ -679,3 +679,26 @@ def test_no_writes_outside_outputs_and_workspace(ce):
         finally:
             os.environ.pop("UPMIX_DIRECT_MIN", None)
     assert canary != canary                        # the canary is a NaN: any arithmetic on it would have shown
+
+
+def test_large_batch_goes_through_in_track_groups(ce):
+    """A batch of more tracks than one four-step wave holds (32) is processed in groups of tracks; every track
+    must equal its own single-track run, bit for bit, in both ways of summing the bands."""
+    import torch
+    sr = 48000
+    ext = quiet(ce.chain_bands, [0, 300, 3000], 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=16384)
+    plan = ce.plan_for(ext)
+    n, tracks = 30000, 40
+    g = torch.Generator(device="cuda").manual_seed(3)
+    L = 0.1 * torch.randn((tracks, n), device="cuda", generator=g)
+    R = 0.1 * torch.randn((tracks, n), device="cuda", generator=g)
+    for direct_min in ("1", str(1 << 60)):
+        os.environ["UPMIX_DIRECT_MIN"] = direct_min
+        try:
+            batch = [t.clone() for t in plan.process(L, R)]
+            for t in (0, 17, 31, 32, 39):
+                single = plan.process(L[t].contiguous(), R[t].contiguous())
+                for bch, sch in zip(batch, single):
+                    assert torch.equal(bch[t], sch), (t, direct_min)
+        finally:
+            os.environ.pop("UPMIX_DIRECT_MIN", None)

@@ -92,6 +92,7 @@ struct Layout {
     int64_t ws_seg = 0;         // per-track stride of a band output in the workspace (floats)
     int64_t band_out_bytes = 0;
     int k3_run = 32;            // large path: hops per column-thread run of col_inv_ola
+    int wave_tracks = 1;        // large path: tracks per wave (a big batch goes through in groups of tracks)
     int wave_hops = 0;          // large path: hops finished per wave
     int wave_frames = 0;        // large path: frames resident per wave (even)
     int64_t a_bytes = 0, b1_bytes = 0, b2_bytes = 0;
@@ -128,15 +129,19 @@ Layout make_layout(const UpmixPlan* p, int64_t seg_len, int n_tracks, bool stage
         // 1.3 MB per hop (10.7 GB for 8192 hops, of 180 GB)
         int64_t wave_total = 8192;
         if (const char* ev = getenv("UPMIX_WAVE_HOPS")) wave_total = std::max(16, atoi(ev));
-        int64_t wh = std::max<int64_t>(16, wave_total / std::max(1, n_tracks));
-        l.k3_run = k3_hops_per_run(std::min<int64_t>(wh, seg_hops), n_tracks);
+        // A wave covers `wave_tracks` tracks x `wave_hops` hops.  Waves shorter than 256 hops waste work (six extra
+        // frames and three warm-up frames per run), so a large batch goes through in groups of tracks instead.
+        const int64_t wt = std::max<int64_t>(1, std::min<int64_t>(n_tracks, wave_total / 256));
+        l.wave_tracks = (int)wt;
+        int64_t wh = std::max<int64_t>(16, wave_total / wt);
+        l.k3_run = k3_hops_per_run(std::min<int64_t>(wh, seg_hops), (int)wt);
         wh = round_up(std::min<int64_t>(wh, round_up(seg_hops, l.k3_run)), l.k3_run);
         l.wave_hops = (int)wh;
         l.wave_frames = (int)wh + 6;
         const int64_t per_frame = (int64_t)p->max_large_n * (int64_t)sizeof(float2);
-        l.a_bytes = round_up((int64_t)n_tracks * l.wave_frames * per_frame, 256);
+        l.a_bytes = round_up(wt * l.wave_frames * per_frame, 256);
         l.b1_bytes = l.a_bytes;
-        l.b2_bytes = round_up((int64_t)n_tracks * (l.wave_frames / 2) * per_frame, 256);
+        l.b2_bytes = round_up(wt * (l.wave_frames / 2) * per_frame, 256);
         l.total += l.a_bytes + l.b1_bytes + l.b2_bytes;
     }
     return l;
@@ -251,20 +256,29 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
             (void)per_frame;
             a.hops_per_run = lay.k3_run;
             const int64_t h_begin = a.hop_begin, h_end = a.hop_end;
-            for (int64_t w0 = h_begin; w0 < h_end; w0 += lay.wave_hops) {
-                const int64_t w1 = std::min<int64_t>(w0 + lay.wave_hops, h_end);
-                const int64_t fa = std::max<int64_t>(0, w0 - 3) & ~1LL;
-                const int64_t fb = (w1 + 1) & ~1LL;
-                w.frame0 = fa;
-                w.n_frames = (int)(fb - fa);
-                if (w.n_frames > lay.wave_frames) return fail(UPMIX_E_INVALID, "internal: wave of %d frames exceeds %d", w.n_frames, lay.wave_frames);
-                SegArgs aw = a;
-                aw.hop_begin = w0;
-                aw.hop_end = w1;
-                const int n_runs = (int)((w1 - w0 + lay.k3_run - 1) / lay.k3_run);
-                CU_CHECK(launch_col_fwd(b, aw, w, n_tracks, st));
-                CU_CHECK(launch_row_mask(b, w, n_tracks, st));
-                CU_CHECK(launch_col_inv_ola(b, aw, w, n_runs, n_tracks, st));
+            for (int t0 = 0; t0 < n_tracks; t0 += lay.wave_tracks) {
+                const int nt = std::min(lay.wave_tracks, n_tracks - t0);
+                SegArgs at = a;                                   // this group of tracks
+                at.in_l += (int64_t)t0 * a.in_stride;
+                at.in_r += (int64_t)t0 * a.in_stride;
+                if (at.out_c) at.out_c += (int64_t)t0 * a.out_stride;
+                at.out_l += (int64_t)t0 * a.out_stride;
+                at.out_r += (int64_t)t0 * a.out_stride;
+                for (int64_t w0 = h_begin; w0 < h_end; w0 += lay.wave_hops) {
+                    const int64_t w1 = std::min<int64_t>(w0 + lay.wave_hops, h_end);
+                    const int64_t fa = std::max<int64_t>(0, w0 - 3) & ~1LL;
+                    const int64_t fb = (w1 + 1) & ~1LL;
+                    w.frame0 = fa;
+                    w.n_frames = (int)(fb - fa);
+                    if (w.n_frames > lay.wave_frames) return fail(UPMIX_E_INVALID, "internal: wave of %d frames exceeds %d", w.n_frames, lay.wave_frames);
+                    SegArgs aw = at;
+                    aw.hop_begin = w0;
+                    aw.hop_end = w1;
+                    const int n_runs = (int)((w1 - w0 + lay.k3_run - 1) / lay.k3_run);
+                    CU_CHECK(launch_col_fwd(b, aw, w, nt, st));
+                    CU_CHECK(launch_row_mask(b, w, nt, st));
+                    CU_CHECK(launch_col_inv_ola(b, aw, w, n_runs, nt, st));
+                }
             }
         }
     }
