@@ -74,7 +74,7 @@ UPMIX_FUSED_CFG_X(256, UPMIX_CFG_256)
 #endif
 UPMIX_FUSED_CFG_X(512, UPMIX_CFG_512)
 #ifndef UPMIX_CFG_1024
-#define UPMIX_CFG_1024 mkplan(16, 16, 4), mkplan(16, 16, 4), mkplan(16, 8, 4), 64, 6
+#define UPMIX_CFG_1024 mkplan(16, 8, 8), mkplan(16, 16, 4), mkplan(16, 8, 4), 64, 6
 #endif
 UPMIX_FUSED_CFG_X(1024, UPMIX_CFG_1024)
 #ifndef UPMIX_CFG_2048
@@ -432,6 +432,8 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
         // FE: per-output overlap-add.  Output r of a last-pass butterfly lies in hop (4 r) / R of the frame.
         constexpr int PINV = MEGA ? PI : PF;
         constexpr int RLI = fft_radix(PINV, fft_num_passes(PINV) - 1), RLH = fft_radix(PH, fft_num_passes(PH) - 1);
+        static_assert(!FE || N < UPMIX_FE_MIN_N || (RLI % 4 == 0 && RLH % 4 == 0),
+                      "fused emit needs last inverse radices that are multiples of 4: an output must lie in one hop of the frame");
         float* __restrict__ oC = outp[0] + (s0 - a.out_begin);
         float* __restrict__ oL = outp[1] + (s0 - a.out_begin);
         float* __restrict__ oR = outp[2] + (s0 - a.out_begin);
