@@ -106,9 +106,9 @@ struct Layout {
 //  * direct: the pipelines run one after the other and add their finished samples straight into the
 //    caller's outputs (the first one stores).  No per-band slots (12 bytes per sample and band, written
 //    and read again), no band-sum pass: 84 -> 60 bytes of HBM traffic per sample for three bands, and
-//    the workspace shrinks to the four-step scratch.  Used from UPMIX_DIRECT_MIN samples up.
+//    the workspace shrinks to the four-step scratch.  Used from UPMIX_DIRECT_MIN samples up (default 3 Mi).
 bool direct_sum(int64_t seg_len, int n_tracks) {
-    int64_t min_samples = 4LL << 20;
+    int64_t min_samples = 3LL << 20;   // crossover measured at ~60 s of one 48 kHz track (profiles/direct_min_sweep.py)
     if (const char* ev = getenv("UPMIX_DIRECT_MIN")) min_samples = atoll(ev);
     return seg_len * (int64_t)n_tracks >= min_samples;
 }
