@@ -70,7 +70,7 @@ UPMIX_FUSED_CFG_X(128, UPMIX_CFG_128)
 #endif
 UPMIX_FUSED_CFG_X(256, UPMIX_CFG_256)
 #ifndef UPMIX_CFG_512
-#define UPMIX_CFG_512 mkplan(16, 8, 4), mkplan(16, 8, 4), mkplan(8, 8, 4), 32, 12
+#define UPMIX_CFG_512 mkplan(16, 8, 4), mkplan(16, 8, 4), mkplan(16, 4, 4), 32, 12
 #endif
 UPMIX_FUSED_CFG_X(512, UPMIX_CFG_512)
 #ifndef UPMIX_CFG_1024
