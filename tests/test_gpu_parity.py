@@ -214,13 +214,15 @@ def test_known_answers_on_device(ce):
     assert float((fl - (l1 + 0.5 * c1)).abs().max()) < 2e-6 and float((fr - (r1 + 0.5 * c1)).abs().max()) < 2e-6
 
 
-def test_five_minute_track_sampled_against_oracle(ce):
-    """cfg 2 shape at a larger size: parity on the first and last seconds and around an interior cut."""
+@pytest.mark.parametrize("seconds", [300, 3600])
+def test_long_track_sampled_against_oracle(ce, seconds):
+    """cfg 2 at a larger size and at BASELINE's full size (1-hour track: direct band sum, 8192-hop four-step waves,
+    whole-wave run lengths): parity on the first and last seconds and around an interior cut."""
     import torch
     sr = 48000
     ext = quiet(ce.chain_bands, [0, 200, 2000], 0.75, ce.make_blackman_harris, sr, "raised_cosine")
     bands = uo.chain([0, 200, 2000], 0.75, uo.blackman_harris, sr)
-    n = 300 * sr + 77
+    n = seconds * sr + 77
     L, R = uo.synth_stereo(n, 1, stress=True)
     out = ce.extract_center_left_right_multi_band_in_memory(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda(), sr, ext)
     out = [o.cpu().numpy() for o in out]
