@@ -214,14 +214,15 @@ def test_known_answers_on_device(ce):
     assert float((fl - (l1 + 0.5 * c1)).abs().max()) < 2e-6 and float((fr - (r1 + 0.5 * c1)).abs().max()) < 2e-6
 
 
-@pytest.mark.parametrize("seconds", [300, 3600])
-def test_long_track_sampled_against_oracle(ce, seconds):
+@pytest.mark.parametrize("seconds,edges", [(300, [0, 200, 2000]), (3600, [0, 200, 2000]), (1800, [0, 30, 120, 480, 1920, 7680])])
+def test_long_track_sampled_against_oracle(ce, seconds, edges):
     """cfg 2 at a larger size and at BASELINE's full size (1-hour track: direct band sum, 8192-hop four-step waves,
-    whole-wave run lengths): parity on the first and last seconds and around an interior cut."""
+    whole-wave run lengths), and main.py's default six bands on half an hour: parity on the first and last seconds
+    and around an interior cut."""
     import torch
     sr = 48000
-    ext = quiet(ce.chain_bands, [0, 200, 2000], 0.75, ce.make_blackman_harris, sr, "raised_cosine")
-    bands = uo.chain([0, 200, 2000], 0.75, uo.blackman_harris, sr)
+    ext = quiet(ce.chain_bands, edges, 0.75, ce.make_blackman_harris, sr, "raised_cosine")
+    bands = uo.chain(edges, 0.75, uo.blackman_harris, sr)
     n = seconds * sr + 77
     L, R = uo.synth_stereo(n, 1, stress=True)
     out = ce.extract_center_left_right_multi_band_in_memory(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda(), sr, ext)
