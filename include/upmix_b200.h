@@ -65,6 +65,12 @@ const char* upmix_last_error(void);
 int upmix_version(void);
 
 int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int device, UpmixPlan** out);
+/* Same, with flags.  UPMIX_PLAN_NO_DECIMATE: band-limited bands (every live bin below 512 and below n_fft/16:
+ * all but the top band of a crossover set) keep the full-size transform kernels instead of the decimated
+ * ones; results agree to float32 rounding.  Block streaming always uses the full-size kernels, so a plan made
+ * with this flag gives bit-identical results through upmix_process and upmix_stream_block. */
+enum { UPMIX_PLAN_NO_DECIMATE = 1 };
+int upmix_plan_create_ex(int n_bands, const UpmixBandDesc* bands, int out_mode, int device, int flags, UpmixPlan** out);
 int upmix_plan_destroy(UpmixPlan* plan);
 int upmix_plan_n_bands(const UpmixPlan* plan);
 /* Bands with identical STFTs (size, hop, both windows) are merged into one pipeline: they share the

@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("UPMIX_B200_LIB") or os.path.join(_HERE, "csrc", "libu
 
 OUT_LSCRS = 0
 OUT_FOLD = 1
+PLAN_NO_DECIMATE = 1      # upmix_plan_create_ex flag: band-limited bands keep the full-size transform kernels
 
 FUSED_MAX_N = 8192
 LARGE_MAX_N = 65536
@@ -54,6 +55,7 @@ def load_library():
     _sig(lib.upmix_last_error, ctypes.c_char_p, [])
     _sig(lib.upmix_version, i32, [])
     _sig(lib.upmix_plan_create, i32, [i32, ctypes.POINTER(_BandDesc), i32, i32, ctypes.POINTER(vp)])
+    _sig(lib.upmix_plan_create_ex, i32, [i32, ctypes.POINTER(_BandDesc), i32, i32, i32, ctypes.POINTER(vp)])
     _sig(lib.upmix_plan_destroy, i32, [vp])
     _sig(lib.upmix_plan_n_bands, i32, [vp])
     _sig(lib.upmix_plan_n_pipelines, i32, [vp])
@@ -81,7 +83,7 @@ def load_library():
     return lib
 
 
-EXPORTS = ("upmix_last_error", "upmix_version", "upmix_plan_create", "upmix_plan_destroy",
+EXPORTS = ("upmix_last_error", "upmix_version", "upmix_plan_create", "upmix_plan_create_ex", "upmix_plan_destroy",
            "upmix_plan_n_bands", "upmix_plan_n_pipelines", "upmix_workspace_bytes", "upmix_segment_halo", "upmix_process",
            "upmix_process_segment", "upmix_stream_state_bytes", "upmix_stream_workspace_bytes",
            "upmix_stream_delay", "upmix_stream_reset", "upmix_stream_block", "upmix_process_host",
@@ -200,7 +202,7 @@ class Plan:
     (n_fft, hop, ana[n_fft], syn[n_fft], gain[n_fft/2+1]) with float32-convertible tables."""
 
     def __init__(self, bands: Sequence[Tuple[int, int, np.ndarray, np.ndarray, np.ndarray]],
-                 out_mode: int = OUT_LSCRS, device: Optional[int] = None):
+                 out_mode: int = OUT_LSCRS, device: Optional[int] = None, flags: int = 0):
         torch = _torch()
         lib = load_library()
         self.device = torch.cuda.current_device() if device is None else int(device)
@@ -218,7 +220,8 @@ class Plan:
             keep += [ana, syn, gain]
             descs[i] = _BandDesc(n_fft, hop, ana.ctypes.data, syn.ctypes.data, gain.ctypes.data)
         handle = ctypes.c_void_p()
-        _check(lib.upmix_plan_create(len(bands), descs, out_mode, self.device, ctypes.byref(handle)))
+        _check(lib.upmix_plan_create_ex(len(bands), descs, out_mode, self.device, int(flags), ctypes.byref(handle)))
+        self.flags = int(flags)
         self._h = handle
         self._lib = lib
         self._ws = None

@@ -244,8 +244,7 @@ class MultiBandExtractorAccu:
                 _as_host_f32(self.synthesis_window), self.band_gain().astype(np.float32))
 
     def _native_plan(self) -> "_native.Plan":
-        key = (self.block_size, self.hop_size, self.f_low, self.f_high, self.sr, self.xover_mode,
-               self.xover_width_low_hz, self.xover_width_high_hz, id(self.analysis_window), id(self.synthesis_window))
+        key = _fingerprint(self) + (_native._torch().cuda.current_device(),)
         if self._plan is None or self._plan_key != key:
             _check_supported([self])
             self._plan = _native.Plan([self.plan_tables()], _native.OUT_LSCRS)
@@ -321,26 +320,45 @@ def _check_supported(band_extractors: Sequence[MultiBandExtractorAccu]) -> None:
             raise NotImplementedError(f"band {i}: block_size={n} > {_native.FUSED_MAX_N} needs 75 % overlap")
 
 
-_PLAN_CACHE: "list" = []      # [(key, extractors, plan)], most recent last
+_PLAN_CACHE: "list" = []      # [(key, plan)], most recent last
+
+
+_RAMPS: dict = {}
+
+
+def _content_key(arr) -> tuple:
+    """Cheap content checksum of a window table (tens of microseconds for 65536 points): the bit patterns'
+    sum and xor plus an index-weighted sum, so that in-place edits, swaps and replacements all change it."""
+    a = _as_host_f32(arr)
+    bits = a.view(np.uint32)
+    ramp = _RAMPS.get(a.shape[0])
+    if ramp is None:
+        ramp = _RAMPS[a.shape[0]] = np.arange(1, a.shape[0] + 1, dtype=np.float64)
+    return (a.shape[0], int(np.add.reduce(bits, dtype=np.uint64)), int(np.bitwise_xor.reduce(bits)) if bits.size else 0,
+            float(np.dot(a.astype(np.float64), ramp)))
 
 
 def _fingerprint(bex) -> tuple:
-    """What a plan depends on: if any of this changes on an extractor, its plan is rebuilt."""
-    return (id(bex), int(bex.block_size), int(bex.hop_size), float(bex.f_low), float(bex.f_high), float(bex.sr),
+    """What a plan depends on: the extractor's parameters, the CONTENT of its two window tables (the reference's
+    attributes are plain arrays, CE:257-258: editing them in place must not leave a stale device copy) and the
+    class that supplies band_gain().  If any of this changes, the plan is rebuilt."""
+    return (int(bex.block_size), int(bex.hop_size), float(bex.f_low), float(bex.f_high), float(bex.sr),
             str(bex.xover_mode), float(bex.xover_width_low_hz), float(bex.xover_width_high_hz),
-            id(bex.analysis_window), id(bex.synthesis_window))
+            _content_key(bex.analysis_window), _content_key(bex.synthesis_window), type(bex).band_gain)
 
 
-def plan_for(band_extractors: Sequence[MultiBandExtractorAccu], out_mode: int = _native.OUT_LSCRS) -> "_native.Plan":
-    """Native plan for a list of extractors (cached while the same, unmodified extractor objects are used)."""
+def plan_for(band_extractors: Sequence[MultiBandExtractorAccu], out_mode: int = _native.OUT_LSCRS,
+             flags: int = 0) -> "_native.Plan":
+    """Native plan for a list of extractors, cached by content (parameters + window tables), output mode, flags
+    and CUDA device.  flags: _native.PLAN_NO_DECIMATE keeps the full-size transform kernels for band-limited bands."""
     torch = _native._torch()
-    key = (tuple(_fingerprint(b) for b in band_extractors), out_mode, torch.cuda.current_device())
-    for k, exts, plan in _PLAN_CACHE:
-        if k == key and all(a is b for a, b in zip(exts, band_extractors)):
+    key = (tuple(_fingerprint(b) for b in band_extractors), out_mode, int(flags), torch.cuda.current_device())
+    for k, plan in _PLAN_CACHE:
+        if k == key:
             return plan
     _check_supported(band_extractors)
-    plan = _native.Plan([b.plan_tables() for b in band_extractors], out_mode)
-    _PLAN_CACHE.append((key, list(band_extractors), plan))
+    plan = _native.Plan([b.plan_tables() for b in band_extractors], out_mode, flags=flags)
+    _PLAN_CACHE.append((key, plan))
     if len(_PLAN_CACHE) > 8:
         _PLAN_CACHE.pop(0)
     return plan

@@ -58,6 +58,13 @@ __device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2
 __device__ __forceinline__ float2 caxpy(float2 a, float s, float2 b) { return make_float2(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y)); }
 #endif
 
+// a * b + c, complex: two packed FMAs
+__device__ __forceinline__ float2 cfma(float2 a, float2 b, float2 c) {
+    const float2 t = __ffma2_rn(a, make_float2(b.x, b.x), c);
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(-b.y, b.y), t);
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
 // multiply by DIR*i  (DIR = -1: forward transform, e^{-i...};  DIR = +1: inverse)
 template <int DIR>
 __device__ __forceinline__ float2 mul_i(float2 a) {

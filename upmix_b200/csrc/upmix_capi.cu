@@ -74,7 +74,8 @@ struct UpmixPlan {
     int64_t halo = 0;           // input margin a time shard needs on each side
     int64_t delay = 0;          // max over bands of n_fft - hop (block streaming latency)
     int sm_count = 148;
-    bool fold_in_freq = false;  // FOLD output and every pipeline fused: the centre is folded per bin
+    bool fold_in_freq = false;  // FOLD output and every pipeline fused or decimated: the centre is folded per bin
+    bool use_dec = true;        // band-limited pipelines take the decimated path (upmix_dec.cu)
     // Pipelines are independent until the band sum, so they are spread over a few plan-owned streams
     // (forked from / joined to the caller's stream with events): co-resident CTAs of different pipelines
     // fill each other's stalls and launch tails.  Pipelines of the four-step path share one scratch and
@@ -96,8 +97,39 @@ struct Layout {
     int wave_hops = 0;          // large path: hops finished per wave
     int wave_frames = 0;        // large path: frames resident per wave (even)
     int64_t a_bytes = 0, b1_bytes = 0, b2_bytes = 0;
+    int64_t dec_off = 0;        // decimated bands: their scratch regions follow the four-step scratch, one per band
     int64_t total = 0;
 };
+
+// Scratch of one decimated band: per frame the masked live bins (3 rows of KP) and, with more than one group of
+// 16 sequences, the groups' partial sums (2 rows each).  A long input goes through in waves of hops (and a large
+// batch in groups of tracks) so that a band's scratch stays within UPMIX_DEC_WS_MB (default 1024 MiB).
+struct DecLayout {
+    int wave_tracks = 1;
+    int64_t wave_hops = 0;      // hops finished per wave; the wave holds wave_hops + 3 frames per track
+    int64_t part_bytes = 0, spec_bytes = 0, total = 0;
+};
+
+DecLayout make_dec_layout(const BandDev& b, int64_t seg_len, int n_tracks) {
+    static const int64_t cap = [] { const char* e = getenv("UPMIX_DEC_WS_MB"); return (int64_t)(e ? std::max(1, atoi(e)) : 1024) << 20; }();
+    DecLayout d;
+    const int64_t groups = b.dec.Q / 16;
+    const int64_t per_frame = ((groups > 1 ? groups * 2 : 0) + 3) * (int64_t)b.dec.KP * (int64_t)sizeof(float2);
+    const int64_t seg_hops = (seg_len + b.hop - 1) / b.hop + 1;      // a segment that starts inside a hop touches one more
+    const int64_t frames_cap = std::max<int64_t>(64, cap / per_frame);
+    if ((seg_hops + 3) * n_tracks <= frames_cap) {
+        d.wave_tracks = n_tracks;
+        d.wave_hops = seg_hops;
+    } else {
+        d.wave_tracks = (int)std::max<int64_t>(1, std::min<int64_t>(n_tracks, frames_cap / 1024));
+        d.wave_hops = std::min<int64_t>(seg_hops, std::max<int64_t>(61, frames_cap / d.wave_tracks - 3));
+    }
+    const int64_t frames = (d.wave_hops + 3) * d.wave_tracks;
+    d.part_bytes = groups > 1 ? round_up(frames * groups * 2 * b.dec.KP * (int64_t)sizeof(float2), 256) : 0;
+    d.spec_bytes = round_up(frames * 3 * b.dec.KP * (int64_t)sizeof(float2), 256);
+    d.total = d.part_bytes + d.spec_bytes;
+    return d;
+}
 
 // Two ways to sum the bands (center_extraction.py:503-511), same float32 additions in the same order:
 //  * staged: every pipeline writes its C/Ls/Rs to a workspace slot, band_sum_kernel adds the slots.  The
@@ -113,15 +145,17 @@ bool direct_sum(int64_t seg_len, int n_tracks) {
     return seg_len * (int64_t)n_tracks >= min_samples;
 }
 
-Layout make_layout(const UpmixPlan* p, int64_t seg_len, int n_tracks, bool staged) {
+Layout make_layout(const UpmixPlan* p, int64_t seg_len, int n_tracks, bool staged, bool chunk_api = false) {
     Layout l;
     l.ws_seg = round_up(std::max<int64_t>(seg_len, 1), 64);
     l.band_out_bytes = staged ? round_up((int64_t)p->bands.size() * 3 * n_tracks * l.ws_seg * (int64_t)sizeof(float), 256) : 0;
     l.total = l.band_out_bytes;
-    if (p->max_large_n) {
-        int64_t hop_min = INT64_MAX;
-        for (const BandDev& b : p->bands)
-            if (b.n_fft > FUSED_MAX_N) hop_min = std::min<int64_t>(hop_min, b.hop);
+    // four-step scratch: bands above 8192 points that do not take the decimated path (the chunk API always takes
+    // the four-step path for them)
+    int64_t hop_min = INT64_MAX;
+    for (const BandDev& b : p->bands)
+        if (b.n_fft > FUSED_MAX_N && (!b.dec.P || chunk_api)) hop_min = std::min<int64_t>(hop_min, b.hop);
+    if (hop_min != INT64_MAX) {
         const int64_t seg_hops = (seg_len + hop_min - 1) / hop_min + 1;
         // hops per wave over all tracks (tuning knob: UPMIX_WAVE_HOPS).  Measured with the final kernels, ms per
         // band-hour for waves of 1024 / 2048 / 4096 / 8192 hops (runs of 64 hops per column thread): 65536 points
@@ -144,6 +178,9 @@ Layout make_layout(const UpmixPlan* p, int64_t seg_len, int n_tracks, bool stage
         l.b2_bytes = round_up(wt * (l.wave_frames / 2) * per_frame, 256);
         l.total += l.a_bytes + l.b1_bytes + l.b2_bytes;
     }
+    l.dec_off = l.total;
+    for (const BandDev& b : p->bands)
+        if (b.dec.P) l.total += make_dec_layout(b, seg_len, n_tracks).total;
     return l;
 }
 
@@ -161,6 +198,56 @@ int pick_hops_per_run(const UpmixPlan* p, int n_fft, int64_t total_hops, int n_t
         const int64_t r = (total_hops + runs_per_track - 1) / runs_per_track;
         if (r <= run_max || waves * slots >= work) return (int)std::max<int64_t>(8, r);
     }
+}
+
+// Hops per run of dec_inv_kernel (a run replays 3 frames): as above, with `ctas_per_run` CTAs sharing a run's hop range
+// (the groups of 16 sequences) -- or two runs sharing a CTA (ctas_per_run = 0: the centre of a 16-sequence band).
+int pick_dec_hops_per_run(const UpmixPlan* p, const BandDev& b, int64_t total_hops, int n_tracks, int ctas_per_run) {
+    static const int run_max = [] { const char* e = getenv("UPMIX_DEC_RUN_MAX"); return e ? std::max(8, atoi(e)) : 256; }();
+    const int64_t ctas = (int64_t)p->sm_count * (1024 / b.dec.P);
+    const int64_t slots = ctas_per_run ? std::max<int64_t>(1, ctas / ctas_per_run) : 2 * ctas;
+    const int64_t work = total_hops * n_tracks;
+    for (int64_t waves = 1;; waves++) {
+        const int64_t runs_per_track = std::max<int64_t>(1, waves * slots / n_tracks);
+        const int64_t r = (total_hops + runs_per_track - 1) / runs_per_track;
+        if (r <= run_max || waves * slots >= work) return (int)std::max<int64_t>(8, r);
+    }
+}
+
+// One decimated band over hops [a.hop_begin, a.hop_end) of every track, in waves: forward + mask of the wave's frames,
+// then the inverse / overlap-add of Ls + i Rs and of the centre.
+int run_dec_band(const UpmixPlan* p, const BandDev& b, const SegArgs& a, int n_tracks, char* scratch, const DecLayout& dl, cudaStream_t st) {
+    const int64_t h_begin = a.hop_begin, h_end = a.hop_end;
+    for (int t0 = 0; t0 < n_tracks; t0 += dl.wave_tracks) {
+        const int nt = std::min(dl.wave_tracks, n_tracks - t0);
+        SegArgs at = a;
+        at.in_l += (int64_t)t0 * a.in_stride;
+        at.in_r += (int64_t)t0 * a.in_stride;
+        if (at.out_c) at.out_c += (int64_t)t0 * a.out_stride;
+        at.out_l += (int64_t)t0 * a.out_stride;
+        at.out_r += (int64_t)t0 * a.out_stride;
+        for (int64_t w0 = h_begin; w0 < h_end; w0 += dl.wave_hops) {
+            const int64_t w1 = std::min<int64_t>(w0 + dl.wave_hops, h_end);
+            DecWave w;
+            w.part = reinterpret_cast<float2*>(scratch);
+            w.spec = reinterpret_cast<float2*>(scratch + dl.part_bytes);
+            w.frame0 = std::max<int64_t>(0, w0 - 3);
+            w.n_frames = (int)(w1 - w.frame0);
+            if (w.n_frames > dl.wave_hops + 3) return fail(UPMIX_E_INVALID, "internal: decimated wave of %d frames exceeds %lld", w.n_frames, (long long)dl.wave_hops + 3);
+            SegArgs aw = at;
+            aw.hop_begin = w0;
+            aw.hop_end = w1;
+            CU_CHECK(launch_dec_fwd(b, aw, w, nt, st));
+            const int groups = b.dec.Q / 16;
+            aw.hops_per_run = pick_dec_hops_per_run(p, b, w1 - w0, nt, groups);
+            CU_CHECK(launch_dec_inv(b, aw, w, (int)((w1 - w0 + aw.hops_per_run - 1) / aw.hops_per_run), nt, false, st));
+            if (!a.fold) {
+                aw.hops_per_run = pick_dec_hops_per_run(p, b, w1 - w0, nt, groups / 2);
+                CU_CHECK(launch_dec_inv(b, aw, w, (int)((w1 - w0 + aw.hops_per_run - 1) / aw.hops_per_run), nt, true, st));
+            }
+        }
+    }
+    return UPMIX_OK;
 }
 
 // Runs every band of the plan over output samples [seg_begin, seg_end) into the band workspace,
@@ -186,13 +273,19 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
     bool first = true;
     bool used[UpmixPlan::N_AUX] = {false, false, false};
     int next_fused = 1;
+    int64_t dec_off = lay.dec_off;
     if (fork) CU_CHECK(cudaEventRecord(p->ev_fork, caller));
 
     for (int bi = 0; bi < nb; bi++) {
         const BandDev& b = p->bands[bi];
+        const bool dec = b.dec.P != 0 && band_state == nullptr;
+        const DecLayout dlay = b.dec.P ? make_dec_layout(b, seg_len, n_tracks) : DecLayout();
+        char* dec_scratch = reinterpret_cast<char*>(workspace) + dec_off;
+        dec_off += dlay.total;
         if (fork) {
-            const int si = b.n_fft > FUSED_MAX_N ? 0 : next_fused;
-            if (b.n_fft <= FUSED_MAX_N) next_fused = next_fused == UpmixPlan::N_AUX - 1 ? 1 : next_fused + 1;
+            const bool own = b.n_fft <= FUSED_MAX_N || dec;     // four-step bands share one scratch, hence one stream
+            const int si = own ? next_fused : 0;
+            if (own) next_fused = next_fused == UpmixPlan::N_AUX - 1 ? 1 : next_fused + 1;
             st = p->aux[si];
             if (!used[si]) {
                 CU_CHECK(cudaStreamWaitEvent(st, p->ev_fork, 0));
@@ -237,7 +330,10 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
         a.hop_begin = a.seg_begin / b.hop;
         a.hop_end = (a.seg_end + b.hop - 1) / b.hop;
         const int64_t total_hops = a.hop_end - a.hop_begin;
-        if (b.n_fft <= FUSED_MAX_N) {
+        if (dec) {
+            const int rc = run_dec_band(p, b, a, n_tracks, dec_scratch, dlay, st);
+            if (rc) return rc;
+        } else if (b.n_fft <= FUSED_MAX_N) {
             if (a.state) {
                 a.hops_per_run = (int)total_hops;              // the ring is carried: one CTA per track
                 CU_CHECK(launch_band_fused(b, a, 1, n_tracks, st));
@@ -312,6 +408,10 @@ const char* upmix_last_error(void) { return g_err; }
 int upmix_version(void) { return 1000; }
 
 int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int device, UpmixPlan** out) {
+    return upmix_plan_create_ex(n_bands, bands, out_mode, device, 0, out);
+}
+
+int upmix_plan_create_ex(int n_bands, const UpmixBandDesc* bands, int out_mode, int device, int flags, UpmixPlan** out) {
     if (!out) return fail(UPMIX_E_INVALID, "out is NULL");
     *out = nullptr;
     if (n_bands < 1 || !bands) return fail(UPMIX_E_INVALID, "need at least one band");
@@ -344,10 +444,35 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
         }
         if (!placed) groups.push_back(std::vector<int>(1, i));
     }
+    // Decimated path (upmix_dec.cu): a pipeline whose live bins all lie below P = 128 / 256 / 512 <= n_fft/16
+    // (75 % overlap) splits its frames into n_fft/P sequences of P points.  dec_p[g] = P, or 0.
+    bool use_dec = !(flags & UPMIX_PLAN_NO_DECIMATE);
+    if (const char* ev = getenv("UPMIX_DEC")) use_dec = use_dec && atoi(ev) != 0;
+    std::vector<int> dec_p(groups.size(), 0), dec_k(groups.size(), 0);
+    bool any_four_step = false;
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        const UpmixBandDesc& d = bands[groups[gi][0]];
+        int top = 0;
+        for (int m : groups[gi])
+            for (int k = d.n_fft / 2; k > top; k--)
+                if (bands[m].gain[k] != 0.f) { top = k; break; }
+        dec_k[gi] = top;
+        const int P = top < 128 ? 128 : top < 256 ? 256 : top < 512 ? 512 : 0;
+        if (use_dec && P && d.hop * 4 == d.n_fft && d.n_fft >= 16 * P) dec_p[gi] = P;
+        if (d.n_fft > FUSED_MAX_N && !dec_p[gi]) any_four_step = true;
+    }
+    // the fold-down epilogue of a plan with four-step bands is applied by the band kernels' copy-out, which the
+    // decimated kernels do not have: such plans keep the older paths
+    if (out_mode == UPMIX_OUT_FOLD && any_four_step) std::fill(dec_p.begin(), dec_p.end(), 0);
     int64_t floats = 0;
-    for (const auto& grp : groups) {
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        const auto& grp = groups[gi];
         const UpmixBandDesc& d = bands[grp[0]];
         floats += round_up(d.n_fft + 1, 64) + round_up(d.n_fft, 64) + (int64_t)grp.size() * round_up(d.n_fft / 2 + 1, 64);
+        if (dec_p[gi]) {
+            const int64_t kp = round_up(dec_k[gi] + 1, 32);
+            floats += 2 * (dec_p[gi] / 16) * 16 + 2 * kp + 2 * (d.n_fft / dec_p[gi] / 16) * kp;
+        }
         if (d.n_fft > FUSED_MAX_N) {
             floats += 2LL * d.n_fft + round_up(2LL * fft_tw_size(row_plan(d.n_fft / COL_R)), 64);
         } else {
@@ -386,9 +511,39 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
                 }
         }
     };
-    for (const auto& grp : groups) {
+    p->use_dec = use_dec;
+    bool four_step = false;
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        const auto& grp = groups[gi];
         const UpmixBandDesc& d = bands[grp[0]];
         BandDev b;
+        memset(&b.dec, 0, sizeof(b.dec));
+        if (dec_p[gi]) {
+            // tables of the decimated path, computed in double: second-pass twiddles of the P-point transform
+            // [k][r] = exp(-2 pi i r k / P); W^k and W^{16 g k}, W = exp(-2 pi i / n_fft), for the live bins
+            const int P = dec_p[gi], Q = d.n_fft / P, R0 = P / 16;
+            const int K = dec_k[gi], KP = (int)round_up(K + 1, 32);
+            b.dec.P = P;
+            b.dec.Q = Q;
+            b.dec.K = K;
+            b.dec.KP = KP;
+            auto put = [&](int64_t at, double turns) {
+                host[at] = (float)cos(-2.0 * M_PI * turns);
+                host[at + 1] = (float)sin(-2.0 * M_PI * turns);
+            };
+            for (int k = 0; k < R0; k++)
+                for (int r = 0; r < 16; r++) put(off + 2 * (k * 16 + r), (double)((r * k) % P) / P);
+            b.dec.tw_last = reinterpret_cast<const float2*>(dbase + off);
+            off += 2 * R0 * 16;
+            for (int k = 0; k < KP; k++) put(off + 2 * k, (double)k / d.n_fft);
+            b.dec.tw_step = reinterpret_cast<const float2*>(dbase + off);
+            off += 2 * KP;
+            for (int g = 0; g < Q / 16; g++)
+                for (int k = 0; k < KP; k++) put(off + 2 * ((int64_t)g * KP + k), (double)(((int64_t)16 * g * k) % d.n_fft) / d.n_fft);
+            b.dec.tw_base = reinterpret_cast<const float2*>(dbase + off);
+            off += 2 * (int64_t)(Q / 16) * KP;
+        }
+        if (d.n_fft > FUSED_MAX_N && !dec_p[gi]) four_step = true;
         b.n_fft = d.n_fft;
         b.hop = d.hop;
         b.tw_fft = b.tw_inv = b.tw_half = b.tw_pack = b.tw_col = nullptr;
@@ -460,7 +615,7 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
         p->delay = std::max<int64_t>(p->delay, d.n_fft - d.hop);
         p->bands.push_back(b);
     }
-    p->fold_in_freq = out_mode == UPMIX_OUT_FOLD && p->max_large_n == 0;
+    p->fold_in_freq = out_mode == UPMIX_OUT_FOLD && !four_step;
     {
         const char* ev = getenv("UPMIX_STREAMS");
         p->multi_stream = !(ev && atoi(ev) == 0);
@@ -627,7 +782,7 @@ int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, con
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (b.n_fft > FUSED_MAX_N) {
         // four-step path: the frame is slot 0 of a two-frame wave, its partner slot is zero
-        const Layout lay = make_layout(plan, b.hop, n_tracks, false);
+        const Layout lay = make_layout(plan, b.hop, n_tracks, false, true);
         if (workspace_bytes < lay.total) return fail(UPMIX_E_WORKSPACE, "workspace too small: %lld given, %lld needed", (long long)workspace_bytes, (long long)lay.total);
         if (plan->out_mode != UPMIX_OUT_LSCRS) return fail(UPMIX_E_UNSUPPORTED, "frame stepping on the four-step path needs Ls/C/Rs output");
         char* scratch = reinterpret_cast<char*>(workspace) + lay.band_out_bytes;

@@ -762,6 +762,7 @@ cudaError_t launch_fma_peak(float* out, int blocks, int iters, cudaStream_t st) 
 // launchers (called from upmix_capi.cu)
 // ---------------------------------------------------------------------------------------------
 static unsigned long long g_launches = 0;
+unsigned long long& launch_counter() { return g_launches; }
 unsigned long long launch_count(bool reset) {
     const unsigned long long v = g_launches;
     if (reset) g_launches = 0;

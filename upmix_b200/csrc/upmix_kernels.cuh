@@ -13,6 +13,17 @@ constexpr int COL_R = 16;         // column radix of the large-N (four-step) pat
 constexpr int FUSED_MAX_N = 8192; // largest STFT size handled by the single-CTA fused kernel
 constexpr int LARGE_MAX_N = 65536;
 
+// Decimated ("band-limited") transform of a band whose live bins all lie below P = n_fft / Q (see upmix_dec.cu):
+// with n = Q p + q the frame splits into Q sequences of P points, and only bins [0, K] and their mirrors are
+// ever needed.  P = 0: the band does not qualify (dense band) or the path is switched off.
+struct DecDev {
+    int P, Q;                  // points per decimated sequence, number of sequences (n_fft = P * Q)
+    int K, KP;                 // highest live bin (max_bin), row length of the spectrum arrays (K + 1 rounded up to 32)
+    const float2* tw_last;     // [R0][16]  exp(-2 pi i r k / P): twiddles of the second (radix-16) pass of the P-point transform
+    const float2* tw_step;     // [KP]      exp(-2 pi i k / n_fft)
+    const float2* tw_base;     // [Q/16][KP] exp(-2 pi i 16 g k / n_fft): twiddle of the first sequence of group g
+};
+
 // Device tables of one band (all in global memory, read-only during processing).
 struct BandDev {
     int n_fft;
@@ -31,6 +42,7 @@ struct BandDev {
     const float2* tw_half;     // per-pass twiddles of the n_fft/2-point transform (fused path)
     const float2* tw_pack;     // [n_fft/2]     exp(-2*pi*i*k/n_fft) for the real-signal packing (fused path)
     const float2* tw_col;      // [16][n_fft/16] exp(-2*pi*i*k1*n2/n_fft), large path only
+    DecDev dec;                // decimated path (dec.P == 0: not used)
 };
 
 // Where the samples are.  Global sample index s of a track lives at in[s - in_begin] for
@@ -65,6 +77,14 @@ struct WaveArgs {
     float2* a;        // [track][n_frames][16][n2]   column-transformed, twiddled input spectra
     float2* b1;       // [track][n_frames][16][n2]   row-inverse-transformed Ls + i*Rs
     float2* b2;       // [track][n_frames/2][16][n2] row-inverse-transformed C(f even) + i*C(f odd)
+    long long frame0;
+    int n_frames;
+};
+
+// Scratch of one wave of the decimated path: frames [frame0, frame0 + n_frames) of every track.
+struct DecWave {
+    float2* part;     // [track][n_frames][Q/16][2][KP]  per-group partial sums of Z[k] and Z[n_fft-k] (Q > 16 only)
+    float2* spec;     // [track][n_frames][3][KP]        masked spectra: Y[k], Y[n_fft-k] of Ls + i Rs, and C[k]
     long long frame0;
     int n_frames;
 };

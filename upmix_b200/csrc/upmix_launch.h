@@ -16,6 +16,10 @@ cudaError_t launch_col_inv_ola(const BandDev& b, const SegArgs& a, const WaveArg
                                cudaStream_t st);
 cudaError_t launch_col_inv_frame(const BandDev& b, const WaveArgs& w, float* ring, float* out_c, float* out_l, float* out_r,
                                  long long out_stride, int n_tracks, cudaStream_t st);
+// decimated path (upmix_dec.cu): forward transform + mask of the wave's frames; inverse + overlap-add of a range of hops
+cudaError_t launch_dec_fwd(const BandDev& b, const SegArgs& a, const DecWave& w, int n_tracks, cudaStream_t st);
+cudaError_t launch_dec_inv(const BandDev& b, const SegArgs& a, const DecWave& w, int n_runs, int n_tracks, bool centre,
+                           cudaStream_t st);
 cudaError_t launch_band_sum(const float* ws, int n_bands, int n_tracks, long long seg_len, long long ws_seg,
                             float* out_c, float* out_l, float* out_r, long long out_stride, int mode,
                             cudaStream_t st);
