@@ -131,11 +131,23 @@ int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, con
                      int n_tracks, int64_t in_stride, float* out_c, float* out_l, float* out_r, int64_t out_stride,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Host-buffer convenience: copies L/R (host float32) to the device, runs upmix_process, copies the
- * outputs back, synchronises.  Allocates and frees its own device memory; for repeated calls use the
- * device-pointer entry points. */
+/* Host buffers: the call main.py makes (MP:43-50, 78-80).  L / R: host arrays of n elements, float32 (UPMIX_F32) or
+ * float64 (UPMIX_F64), element strides stride_l / stride_r (main.py passes the two columns of an interleaved float64
+ * [n][2] array: stride 2); pageable or pinned.  out_*: host float32 [n], caller-owned (pageable or pinned; out_c may
+ * be NULL in FOLD mode).  The track goes through in time segments -- converted and uploaded chunk by chunk by
+ * n_threads workers (0: UPMIX_HOST_THREADS or half the cores, at most 8), processed with upmix_process_segment as soon
+ * as a segment's halo'd input has landed, downloaded and copied out by n_threads more workers -- so conversion, both
+ * copy directions and the kernels overlap; the result is bit-identical to upmix_process on the same samples.  Pinned
+ * buffers (cudaHostAlloc / cudaHostRegister) are used in place.  Device buffers and pinned staging are cached in the
+ * plan between calls (one host call at a time per plan); upmix_plan_release_host frees them.  Returns when the outputs
+ * are complete. */
+enum { UPMIX_F32 = 0, UPMIX_F64 = 1 };
+int upmix_process_host_ex(const UpmixPlan* plan, const void* L, const void* R, int dtype, int64_t stride_l, int64_t stride_r,
+                          int64_t n_samples, float* out_c, float* out_l, float* out_r, int n_threads);
+/* Same with contiguous float32 input and the default thread count. */
 int upmix_process_host(const UpmixPlan* plan, const float* L, const float* R, int64_t n_samples, float* out_c,
                        float* out_l, float* out_r);
+int upmix_plan_release_host(UpmixPlan* plan);
 
 /* main.py's tail on the device.  upmix_peak3: peaks3[0..2] (device) = max|C|, max|Ls|, max|Rs| over n
  * samples (main.py:85-88); workspace of upmix_peak_workspace_bytes() device bytes.  upmix_export_mix:

@@ -95,14 +95,22 @@ def test_bela_mode_vs_compiled_reference_fixture(ce, golden_dir):
         ol, orr = quiet(bela.bela_offline, L, R, 48000.0, hw)
         peak = float(max(np.abs(L).max(), np.abs(R).max()))
         assert_parity((g["ref_outL"], g["ref_outR"]), (ol, orr), peak, names=("outL", "outR"), what=f"bela hw{hw}")
-        # block-by-block streaming gives the same stream, bit for bit
+        # block-by-block streaming gives the same stream
         up = bela.MultiBandUpmix()
         up.setThresholdMultiplier(bela.THRESHOLD_MULTI)
         quiet(up.setup, hw, 48000.0, 4, [0.0, 500.0, 2000.0, 8000.0, 24000.0])
         blocks = [up.process(L[i:i + hw], R[i:i + hw], hw) for i in range(0, len(L), hw)]
         sl = np.concatenate([b[0] for b in blocks])
         sr_ = np.concatenate([b[1] for b in blocks])
-        assert np.array_equal(sl, ol) and np.array_equal(sr_, orr)
+        assert_parity((g["ref_outL"], g["ref_outR"]), (sl, sr_), peak, names=("outL", "outR"), what=f"bela stream hw{hw}")
+        # ... to float32 rounding against the offline call (whose band-limited bands take the decimated kernels) and
+        # bit for bit against an offline plan that keeps the full-size kernels, the ones block streaming runs
+        assert max(np.max(np.abs(sl - ol)), np.max(np.abs(sr_ - orr))) < 1e-6
+        from upmix_b200 import _native
+        n = (len(L) // hw) * hw
+        plan = ce.plan_for(up.bands, _native.OUT_FOLD, _native.PLAN_NO_DECIMATE)
+        fl, fr = ce._run_plan(plan, L[:n], R[:n])
+        assert np.array_equal(sl[3 * hw:], fl[:n - 3 * hw]) and np.array_equal(sr_[3 * hw:], fr[:n - 3 * hw])
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -274,15 +282,30 @@ def test_pipelined_host_path_is_bit_identical(ce, monkeypatch):
     host = ce.extract_center_left_right_multi_band_in_memory(hl, hr, sr, ext)
     for d, h in zip(dev, host):
         assert not h.is_cuda and torch.equal(d.cpu(), h)
-    host2 = plan.process_host_tensors(hl, hr, segment_seconds=7.0)
+    monkeypatch.setenv("UPMIX_HOST_SEG", str(7 * sr))        # fixed 7 s segments
+    host2 = plan.process_host_tensors(hl, hr)
     for d, h in zip(dev, host2):
         assert torch.equal(d.cpu(), h)
     # full segments above the direct-sum threshold, a shorter last one below it (it stages its bands):
     # one workspace sized for the full segment must serve both
     monkeypatch.setenv("UPMIX_DIRECT_MIN", str(6 * sr))
-    host3 = plan.process_host_tensors(hl, hr, segment_seconds=7.0)
+    host3 = plan.process_host_tensors(hl, hr)
     for d, h in zip(dev, host3):
         assert torch.equal(d.cpu(), h)
+    # results are fresh allocations: a second call must not overwrite the first one's tensors
+    keep = [h.clone() for h in host3]
+    other = plan.process_host_tensors(hr, hl)
+    assert all(torch.equal(k, h) for k, h in zip(keep, host3)) and not torch.equal(other[1], host3[1])
+    # the call main.py makes (main.py:43-50, 78-80): float64 strided views of one interleaved array, pageable memory
+    monkeypatch.delenv("UPMIX_HOST_SEG")
+    monkeypatch.delenv("UPMIX_DIRECT_MIN")
+    wave = np.stack([L, R], axis=1).astype(np.float64)
+    got = ce.extract_center_left_right_multi_band_in_memory(wave[:, 0], wave[:, 1], sr, ext)
+    for d, g in zip(dev, got):
+        assert isinstance(g, np.ndarray) and g.dtype == np.float32 and np.array_equal(d.cpu().numpy(), g)
+    got32 = ce.extract_center_left_right_multi_band_in_memory(L[::-1][::-1], R, sr, ext)     # pageable float32
+    for d, g in zip(dev, got32):
+        assert np.array_equal(d.cpu().numpy(), g)
 
 
 def test_sharding_extract_segment_matches_whole(ce):

@@ -70,6 +70,8 @@ def load_library():
     _sig(lib.upmix_stream_reset, i32, [vp, vp, i32, vp])
     _sig(lib.upmix_stream_block, i32, [vp, vp, i64, vp, vp, i32, i32, i64, vp, vp, vp, i64, vp, i64, vp])
     _sig(lib.upmix_process_host, i32, [vp, vp, vp, i64, vp, vp, vp])
+    _sig(lib.upmix_process_host_ex, i32, [vp, vp, vp, i32, i64, i64, i64, vp, vp, vp, i32])
+    _sig(lib.upmix_plan_release_host, i32, [vp])
     _sig(lib.upmix_frame_step, i32, [vp, vp, i64, vp, vp, i32, i64, vp, vp, vp, i64, vp, i64, vp])
     _sig(lib.upmix_peak_workspace_bytes, i64, [])
     _sig(lib.upmix_peak3, i32, [vp, vp, vp, i64, vp, vp, i64, vp])
@@ -87,6 +89,7 @@ EXPORTS = ("upmix_last_error", "upmix_version", "upmix_plan_create", "upmix_plan
            "upmix_plan_n_bands", "upmix_plan_n_pipelines", "upmix_workspace_bytes", "upmix_segment_halo", "upmix_process",
            "upmix_process_segment", "upmix_stream_state_bytes", "upmix_stream_workspace_bytes",
            "upmix_stream_delay", "upmix_stream_reset", "upmix_stream_block", "upmix_process_host",
+           "upmix_process_host_ex", "upmix_plan_release_host",
            "upmix_frame_step", "upmix_debug_launch_count", "upmix_measure_fp32_tflops",
            "upmix_peak_workspace_bytes", "upmix_peak3", "upmix_export_mix", "upmix_pcm16_to_planar",
            "upmix_stereo_to_pcm16", "upmix_fir_filter")
@@ -311,98 +314,59 @@ class Plan:
     def stream_open(self, n_tracks: int = 1):
         return Stream(self, n_tracks)
 
-    # -- host tensors (pinned staging), pipelined over time segments ---------------------------------
-    def process_host_tensors(self, L, R, segment_seconds: float = 0.0, sample_rate: float = 48000.0):
-        """L, R: float32 CPU torch tensors [n] (pinned memory makes the copies asynchronous).  The
-        track is cut into time segments (multiples of the largest hop); input chunks go up on one
-        stream, each segment is processed as soon as its halo'd input has landed
-        (upmix_process_segment: bit-identical to one whole-track call) and its outputs come down on a
-        third stream, so H2D, kernels and D2H overlap.  segment_seconds = 0 picks segments of about 90 s
-        (measured on B200, 1-hour track, profiles/e2e_sweep.py: 450 s segments 48.2 ms, 120 s 43.1 ms,
-        60 s 42.9 ms, 30 s 45.4 ms -- the device-to-host copy alone takes 38.9 ms; shorter segments let
-        it start earlier, very short ones under-fill the GPU).  Returns pinned CPU tensors,
-        overwritten by the next call on this plan."""
-        torch = _torch()
-        if L.dtype != torch.float32 or R.dtype != torch.float32 or L.dim() != 1 or L.shape != R.shape:
-            raise TypeError("L and R must be 1-D float32 CPU tensors of equal length")
-        n = L.shape[0]
-        n_out = 3 if self.out_mode == OUT_LSCRS else 2
-        dev = torch.device(f"cuda:{self.device}")
-        cache = getattr(self, "_host_cache", None)
-        if cache is None or cache[0] != n:
-            self._host_cache = cache = (n, torch.empty((2, n), dtype=torch.float32, device=dev),
-                                        torch.empty((n_out, n), dtype=torch.float32, device=dev),
-                                        torch.empty((n_out, n), dtype=torch.float32, pin_memory=True),
-                                        torch.cuda.Stream(dev), torch.cuda.Stream(dev))
-        _, d_in, d_out, h_out, s_up, s_down = cache
-        main = torch.cuda.current_stream(dev)
-        align = max(self.hops)
-        if segment_seconds <= 0:
-            n_seg = max(1, min(64, int(round(n / (90.0 * sample_rate)))))
-            seg = -(-n // n_seg)
-        else:
-            seg = int(segment_seconds * sample_rate)
-        seg = max(align, -(-seg // align) * align)
-        # the first segments are short and double up to `seg`: the device-to-host copy -- the longest stage
-        # of the pipeline -- starts after a few hundred microseconds instead of after two full chunks
-        bounds, pos, step = [0], 0, seg
-        if segment_seconds <= 0:
-            step = max(align, -(-int(8.0 * sample_rate) // align) * align)
-        while pos < n:
-            pos = min(n, pos + step)
-            bounds.append(pos)
-            step = min(seg, 2 * step)
-        # input chunks: chunk i carries samples [bounds[i], bounds[i+1]); segment i needs chunks up to
-        # the one holding sample min(n, bounds[i+1] + halo) - 1
-        s_up.wait_stream(main)
-        s_down.wait_stream(main)
-        up_done = []
-        for a, b in zip(bounds[:-1], bounds[1:]):
-            with torch.cuda.stream(s_up):
-                d_in[0, a:b].copy_(L[a:b], non_blocking=True)
-                d_in[1, a:b].copy_(R[a:b], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(s_up)
-            up_done.append(ev)
-        wsb = self.workspace_bytes(max([b - a for a, b in zip(bounds[:-1], bounds[1:])] or [1]), 1)
-        ws = self._workspace(wsb)
-        import bisect
-        for i, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
-            need = min(n, b + self.halo) - 1
-            last_chunk = min(len(up_done) - 1, bisect.bisect_right(bounds, need) - 1)
-            main.wait_event(up_done[last_chunk])
-            oc, ol, orr = (d_out[0, a:b], d_out[1, a:b], d_out[2, a:b]) if n_out == 3 else (None, d_out[0, a:b], d_out[1, a:b])
-            with torch.cuda.device(dev):
-                _check(self._lib.upmix_process_segment(
-                    self._h, d_in[0].data_ptr(), d_in[1].data_ptr(), 0, n, n, a, b, 1, n,
-                    oc.data_ptr() if oc is not None else None, ol.data_ptr(), orr.data_ptr(), n,
-                    ws.data_ptr(), wsb, main.cuda_stream))
-            ev = torch.cuda.Event()
-            ev.record(main)
-            with torch.cuda.stream(s_down):
-                s_down.wait_event(ev)
-                for ch in range(n_out):
-                    h_out[ch, a:b].copy_(d_out[ch, a:b], non_blocking=True)
-        main.wait_stream(s_down)
-        main.synchronize()
-        return tuple(h_out[i] for i in range(n_out))
+    # -- host buffers: upmix_process_host_ex (chunked convert / H2D / kernels / D2H pipeline in the library) -------
+    def release_host(self):
+        """Free the device buffers and pinned staging the host-buffer calls cache in the plan."""
+        _check(self._lib.upmix_plan_release_host(self._h))
 
-    # -- host buffers ----------------------------------------------------------------------------
-    def process_host(self, L: np.ndarray, R: np.ndarray):
-        """numpy float32 in, numpy float32 out, through upmix_process_host (H2D + kernels + D2H)."""
-        _torch()
-        L = np.ascontiguousarray(L, dtype=np.float32)
-        R = np.ascontiguousarray(R, dtype=np.float32)
-        if L.ndim != 1 or L.shape != R.shape:
-            raise ValueError("L and R must be 1-D arrays of equal length")
-        n = L.shape[0]
+    def _host_call(self, lp: int, rp: int, dtype: int, sl: int, sr: int, n: int, n_threads: int = 0):
+        """Runs the host pipeline into FRESH pinned output tensors (torch's caching host allocator hands back
+        blocks of results that have been dropped, never one that is still referenced)."""
+        torch = _torch()
         n_out = 3 if self.out_mode == OUT_LSCRS else 2
-        outs = [np.empty(n, dtype=np.float32) for _ in range(n_out)]
-        ptrs = [o.ctypes.data for o in outs]
+        out = torch.empty((n_out, n), dtype=torch.float32, pin_memory=True)
+        ptrs = [out[i].data_ptr() for i in range(n_out)]
         if n_out == 2:
             ptrs = [None] + ptrs
-        _check(self._lib.upmix_process_host(self._h, L.ctypes.data, R.ctypes.data, n, *ptrs))
-        return tuple(outs)
+        with torch.cuda.device(self.device):
+            _check(self._lib.upmix_process_host_ex(self._h, lp, rp, dtype, sl, sr, n, ptrs[0], ptrs[1], ptrs[2], int(n_threads)))
+        return out
+
+    def process_host_tensors(self, L, R, n_threads: int = 0):
+        """L, R: 1-D float32 / float64 CPU torch tensors (any stride; pinned float32 is used in place).  Returns
+        freshly allocated pinned float32 CPU tensors; bit-identical to a device-resident call."""
+        torch = _torch()
+        if L.dtype not in (torch.float32, torch.float64) or R.dtype != L.dtype or L.dim() != 1 or L.shape != R.shape:
+            raise TypeError("L and R must be 1-D float32 or float64 CPU tensors of equal length")
+        n = L.shape[0]
+        n_out = 3 if self.out_mode == OUT_LSCRS else 2
+        if n == 0:
+            return tuple(torch.empty(0, dtype=torch.float32) for _ in range(n_out))
+        if L.stride(0) < 1 or R.stride(0) < 1:
+            L, R = L.contiguous(), R.contiguous()
+        out = self._host_call(L.data_ptr(), R.data_ptr(), 0 if L.dtype == torch.float32 else 1, L.stride(0), R.stride(0), n,
+                              n_threads)
+        return tuple(out[i] for i in range(n_out))
+
+    def process_host(self, L: np.ndarray, R: np.ndarray, n_threads: int = 0):
+        """numpy in (float32 or float64, any positive stride -- e.g. the two columns of the interleaved float64
+        array sf.read returns, main.py:43-50), fresh float32 numpy arrays out (views of pinned memory)."""
+        _torch()
+        L, R = np.asarray(L), np.asarray(R)
+        if L.ndim != 1 or L.shape != R.shape:
+            raise ValueError("L and R must be 1-D arrays of equal length")
+        if L.dtype != R.dtype or L.dtype not in (np.float32, np.float64):
+            L, R = np.ascontiguousarray(L, dtype=np.float32), np.ascontiguousarray(R, dtype=np.float32)
+        item = L.dtype.itemsize
+        if L.shape[0] and (L.strides[0] < item or R.strides[0] < item or L.strides[0] % item or R.strides[0] % item):
+            L, R = np.ascontiguousarray(L), np.ascontiguousarray(R)
+        n = L.shape[0]
+        n_out = 3 if self.out_mode == OUT_LSCRS else 2
+        if n == 0:
+            return tuple(np.zeros(0, dtype=np.float32) for _ in range(n_out))
+        out = self._host_call(L.ctypes.data, R.ctypes.data, 0 if L.dtype == np.float32 else 1, L.strides[0] // item,
+                              R.strides[0] // item, n, n_threads)
+        return tuple(out[i].numpy() for i in range(n_out))
 
 
 class Stream:

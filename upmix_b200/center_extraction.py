@@ -368,19 +368,13 @@ def _run_plan(plan: "_native.Plan", L, R) -> tuple:
     torch = _native._torch()
     if _is_cuda_tensor(L):
         return plan.process(L, R)
-    if isinstance(L, torch.Tensor):                 # host tensors (pinned): staged copies, tensors back
-        return plan.process_host_tensors(L.to(torch.float32), R.to(torch.float32))
-    Lh, Rh = _as_host_f32(L), _as_host_f32(R)
-    if Lh.ndim != 1 or Lh.shape != Rh.shape:
-        raise ValueError("L and R must be 1-D signals of equal length")
-    if Lh.shape[0] == 0:
-        z = np.zeros(0, dtype=np.float32)
-        return tuple(z.copy() for _ in range(3 if plan.out_mode == _native.OUT_LSCRS else 2))
-    dev = f"cuda:{plan.device}"
-    dl = torch.from_numpy(Lh).to(dev, non_blocking=True)
-    dr = torch.from_numpy(Rh).to(dev, non_blocking=True)
-    out = plan.process(dl, dr)
-    return tuple(o.cpu().numpy() for o in out)
+    if isinstance(L, torch.Tensor):                 # host tensors: the library's host pipeline, pinned tensors back
+        if L.dtype not in (torch.float32, torch.float64) or R.dtype != L.dtype:
+            L, R = L.to(torch.float32), R.to(torch.float32)
+        return plan.process_host_tensors(L, R)
+    # numpy (what main.py passes: float64 strided views of the interleaved array sf.read returns, MP:43-50):
+    # converted, uploaded, processed and downloaded chunk by chunk inside upmix_process_host_ex
+    return plan.process_host(L, R)
 
 
 ###############################################################################

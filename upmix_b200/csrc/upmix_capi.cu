@@ -16,20 +16,23 @@
 #include "fft_device.cuh"
 #include "upmix_kernels.cuh"
 #include "upmix_launch.h"
+#include "upmix_plan.h"
 
 using namespace upmix;
 
-namespace {
-
 thread_local char g_err[512] = "";
 
-int fail(int code, const char* fmt, ...) {
+int upmix_fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
 }
+
+namespace {
+
+#define fail upmix_fail
 
 #define CU_CHECK(expr)                                                                            \
     do {                                                                                          \
@@ -63,29 +66,6 @@ int k3_hops_per_run(int64_t wave_hops, int n_tracks) {
 }
 
 }  // namespace
-
-struct UpmixPlan {
-    int device = 0;
-    int out_mode = 0;
-    std::vector<BandDev> bands;  // one entry per pipeline: bands with identical STFTs are merged
-    int n_bands_in = 0;          // bands the caller described
-    void* tables = nullptr;     // one device allocation holding every table
-    int max_large_n = 0;        // largest n_fft handled by the four-step path (0: none)
-    int64_t halo = 0;           // input margin a time shard needs on each side
-    int64_t delay = 0;          // max over bands of n_fft - hop (block streaming latency)
-    int sm_count = 148;
-    bool fold_in_freq = false;  // FOLD output and every pipeline fused or decimated: the centre is folded per bin
-    bool use_dec = true;        // band-limited pipelines take the decimated path (upmix_dec.cu)
-    // Pipelines are independent until the band sum, so they are spread over a few plan-owned streams
-    // (forked from / joined to the caller's stream with events): co-resident CTAs of different pipelines
-    // fill each other's stalls and launch tails.  Pipelines of the four-step path share one scratch and
-    // therefore one stream.
-    static constexpr int N_AUX = 3;
-    cudaStream_t aux[N_AUX] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr;
-    cudaEvent_t ev_join[N_AUX] = {nullptr, nullptr, nullptr};
-    bool multi_stream = false;
-};
 
 namespace {
 
@@ -643,6 +623,7 @@ int upmix_plan_destroy(UpmixPlan* plan) {
         if (plan->ev_join[si]) cudaEventDestroy(plan->ev_join[si]);
     }
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    upmix_host_ctx_destroy(plan->host);
     cudaFree(plan->tables);
     delete plan;
     return UPMIX_OK;
@@ -659,13 +640,17 @@ int64_t upmix_workspace_bytes(const UpmixPlan* plan, int64_t seg_len, int n_trac
     // whose last one is shorter): long segments sum directly and need only the four-step scratch, which
     // grows with the length; segments below the direct-sum threshold stage their bands, so the staged
     // layout of the longest such segment is covered as well.
-    if (!direct_sum(seg_len, n_tracks)) return make_layout(plan, seg_len, n_tracks, true).total;
+    // upmix_frame_step on a band above 8192 points always takes the four-step path: cover its scratch as well
+    int64_t chunk_api = 0;
+    if (plan->bands.size() == 1 && plan->bands[0].n_fft > FUSED_MAX_N && plan->bands[0].dec.P && seg_len <= plan->bands[0].hop)
+        chunk_api = make_layout(plan, seg_len, n_tracks, false, true).total;
+    if (!direct_sum(seg_len, n_tracks)) return std::max(chunk_api, make_layout(plan, seg_len, n_tracks, true).total);
     int64_t lo = 0, hi = seg_len;                      // largest staged length: direct_sum is monotonic in seg_len
     while (lo < hi) {
         const int64_t mid = lo + (hi - lo + 1) / 2;
         if (direct_sum(mid, n_tracks)) hi = mid - 1; else lo = mid;
     }
-    return std::max(make_layout(plan, seg_len, n_tracks, false).total, make_layout(plan, lo, n_tracks, true).total);
+    return std::max(chunk_api, std::max(make_layout(plan, seg_len, n_tracks, false).total, make_layout(plan, lo, n_tracks, true).total));
 }
 
 int64_t upmix_segment_halo(const UpmixPlan* plan) { return plan ? plan->halo : fail(UPMIX_E_INVALID, "plan is NULL"); }
@@ -897,48 +882,6 @@ int upmix_measure_fp32_tflops(int device, double* tflops, int* sm_count) {
     cudaFree(out);
     *tflops = best;
     return UPMIX_OK;
-}
-
-int upmix_process_host(const UpmixPlan* plan, const float* L, const float* R, int64_t n_samples, float* out_c,
-                       float* out_l, float* out_r) {
-    if (!plan) return fail(UPMIX_E_INVALID, "plan is NULL");
-    if (!L || !R || !out_l || !out_r || (plan->out_mode == UPMIX_OUT_LSCRS && !out_c)) return fail(UPMIX_E_INVALID, "NULL buffer");
-    if (n_samples <= 0) return n_samples == 0 ? UPMIX_OK : fail(UPMIX_E_INVALID, "negative length");
-    DeviceGuard guard(plan->device);
-    const int64_t nal = round_up(n_samples, 64);
-    const int64_t wsb = upmix_workspace_bytes(plan, n_samples, 1);
-    const int n_out = plan->out_mode == UPMIX_OUT_LSCRS ? 3 : 2;
-    float* dev = nullptr;
-    void* ws = nullptr;
-    cudaStream_t st = nullptr;
-    int rc = UPMIX_OK;
-    cudaError_t e = cudaMalloc(&dev, (size_t)(2 + n_out) * nal * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&ws, (size_t)wsb);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-    if (e != cudaSuccess) rc = fail(UPMIX_E_CUDA, "allocation failed: %s", cudaGetErrorString(e));
-    if (rc == UPMIX_OK) {
-        float* dl = dev;
-        float* dr = dev + nal;
-        float* o0 = dev + 2 * nal;      // FOLD: out_l, out_r;  LSCRS: out_c, out_l, out_r
-        float* oc = n_out == 3 ? o0 : nullptr;
-        float* ol = n_out == 3 ? o0 + nal : o0;
-        float* orr = ol + nal;
-        e = cudaMemcpyAsync(dl, L, (size_t)n_samples * sizeof(float), cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(dr, R, (size_t)n_samples * sizeof(float), cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) rc = fail(UPMIX_E_CUDA, "H2D failed: %s", cudaGetErrorString(e));
-        if (rc == UPMIX_OK) rc = upmix_process(plan, dl, dr, n_samples, 1, nal, oc, ol, orr, nal, ws, wsb, st);
-        if (rc == UPMIX_OK) {
-            if (oc) e = cudaMemcpyAsync(out_c, oc, (size_t)n_samples * sizeof(float), cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(out_l, ol, (size_t)n_samples * sizeof(float), cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(out_r, orr, (size_t)n_samples * sizeof(float), cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) rc = fail(UPMIX_E_CUDA, "D2H / sync failed: %s", cudaGetErrorString(e));
-        }
-    }
-    if (st) cudaStreamDestroy(st);
-    cudaFree(ws);
-    cudaFree(dev);
-    return rc;
 }
 
 }  // extern "C"

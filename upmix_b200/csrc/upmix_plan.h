@@ -1,0 +1,41 @@
+// Internal: the plan object behind the C ABI (include/upmix_b200.h), shared by upmix_capi.cu (plans, scheduling)
+// and upmix_host.cu (host-buffer pipeline).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "upmix_kernels.cuh"
+
+struct UpmixHostCtx;
+
+struct UpmixPlan {
+    int device = 0;
+    int out_mode = 0;
+    std::vector<upmix::BandDev> bands;  // one entry per pipeline: bands with identical STFTs are merged
+    int n_bands_in = 0;          // bands the caller described
+    void* tables = nullptr;     // one device allocation holding every table
+    int max_large_n = 0;        // largest n_fft handled by the four-step path (0: none)
+    int64_t halo = 0;           // input margin a time shard needs on each side
+    int64_t delay = 0;          // max over bands of n_fft - hop (block streaming latency)
+    int sm_count = 148;
+    bool fold_in_freq = false;  // FOLD output and every pipeline fused or decimated: the centre is folded per bin
+    bool use_dec = true;        // band-limited pipelines take the decimated path (upmix_dec.cu)
+    // Pipelines are independent until the band sum, so they are spread over a few plan-owned streams
+    // (forked from / joined to the caller's stream with events): co-resident CTAs of different pipelines
+    // fill each other's stalls and launch tails.  Pipelines of the four-step path share one scratch and
+    // therefore one stream.
+    static constexpr int N_AUX = 3;
+    cudaStream_t aux[N_AUX] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[N_AUX] = {nullptr, nullptr, nullptr};
+    bool multi_stream = false;
+    UpmixHostCtx* host = nullptr;   // buffers of upmix_process_host_ex, created on first use
+};
+
+
+// sets upmix_last_error() for the calling thread and returns `code`
+int upmix_fail(int code, const char* fmt, ...);
+// frees the host pipeline's cached buffers (upmix_host.cu); called by upmix_plan_destroy
+void upmix_host_ctx_destroy(UpmixHostCtx* ctx);
