@@ -344,6 +344,26 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
         }
         __syncthreads();
 
+        // the live bins this thread expands for the NEXT frame: pull them from L2 into L1 while the passes run
+        // (the expansion's first multiply waited on these loads for 14 % of the kernel's stall samples)
+        if (i + 1 < n_iter) {
+#pragma unroll
+            for (int s = 0; s < NST; s++) {
+                const long long fn = fs[s] + 1;
+                if (fn >= 0 && fn < h1s[s]) {
+                    const float2* __restrict__ sp = w.spec + (((long long)track * w.n_frames + (fn - w.frame0)) * 3 + (CM == DEC_Y ? 0 : 2)) * KP;
+                    if (has1) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + es));
+                        if (CM == DEC_Y) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + KP + es));
+                    }
+                    if (has2) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + es2));
+                        if (CM == DEC_Y) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + KP + es2));
+                    }
+                }
+            }
+        }
+
         // ---- inverse pass 0 (radix R0, no twiddles), in place ----
         {
             float2 v[IT0][R0];
@@ -378,6 +398,18 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
         for (int it = 0; it < 2; it++) {
             const int j = jb + it * JS;
             float2 u[16], tw[16];
+            const int m1 = Q * j + qoff1, m2 = Q * j + qoff2;     // + r * R0 * Q: compile-time offsets
+            // this band adds to what the outputs hold (the bands before it, in band order): those values are requested
+            // first and wait in registers while the butterfly runs
+            float2 prev[4];
+            if (ACCUM) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int n1 = m1 + r * R0 * Q, n2 = m2 + r * R0 * Q;
+                    prev[r].x = (n1 >= e_lo && n1 < e_hi) ? __ldcs(d1 + n1) : 0.f;
+                    prev[r].y = (n2 >= e_lo && n2 < e_hi) ? __ldcs(d2 + n2) : 0.f;
+                }
+            }
             const float2* __restrict__ src = buf + j * DEC_QS + q;
 #pragma unroll
             for (int r = 0; r < 16; r++) u[r] = src[r * NB1 * DEC_QS];
@@ -385,7 +417,6 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
 #pragma unroll
             for (int r = 1; r < 16; r++) u[r] = cmul(u[r], cconj(tw[r]));
             Dft<16, +1>::run(u);
-            const int m1 = Q * j + qoff1, m2 = Q * j + qoff2;     // + r * R0 * Q: compile-time offsets
             const float* __restrict__ syn1 = syn + m1;
             const float* __restrict__ syn2 = syn + m2;
 #pragma unroll
@@ -395,8 +426,8 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
                 if (r < 4) {
                     const float2 tot = __ffma2_rn(u[r], ww, acc[it][r]);
                     const int n1 = m1 + r * R0 * Q, n2 = m2 + r * R0 * Q;
-                    if (n1 >= e_lo && n1 < e_hi) __stcs(d1 + n1, ACCUM ? __ldcs(d1 + n1) + tot.x : tot.x);
-                    if (n2 >= e_lo && n2 < e_hi) __stcs(d2 + n2, ACCUM ? __ldcs(d2 + n2) + tot.y : tot.y);
+                    if (n1 >= e_lo && n1 < e_hi) __stcs(d1 + n1, ACCUM ? prev[r].x + tot.x : tot.x);
+                    if (n2 >= e_lo && n2 < e_hi) __stcs(d2 + n2, ACCUM ? prev[r].y + tot.y : tot.y);
                 }
                 if (r >= 4 && r < 12) acc[it][r - 4] = __ffma2_rn(u[r], ww, acc[it][r]);
                 if (r >= 12) acc[it][r - 4] = __fmul2_rn(u[r], ww);
