@@ -135,7 +135,7 @@ int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, con
  * float64 (UPMIX_F64), element strides stride_l / stride_r (main.py passes the two columns of an interleaved float64
  * [n][2] array: stride 2); pageable or pinned.  out_*: host float32 [n], caller-owned (pageable or pinned; out_c may
  * be NULL in FOLD mode).  The track goes through in time segments -- converted and uploaded chunk by chunk by
- * n_threads workers (0: UPMIX_HOST_THREADS or half the cores, at most 8), processed with upmix_process_segment as soon
+ * n_threads workers (0: UPMIX_HOST_THREADS, or the cores divided by LOCAL_WORLD_SIZE, at most 16), processed with upmix_process_segment as soon
  * as a segment's halo'd input has landed, downloaded and copied out by n_threads more workers -- so conversion, both
  * copy directions and the kernels overlap; the result is bit-identical to upmix_process on the same samples.  Pinned
  * buffers (cudaHostAlloc / cudaHostRegister) are used in place.  Device buffers and pinned staging are cached in the

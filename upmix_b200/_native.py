@@ -277,8 +277,9 @@ class Plan:
         n_out = 3 if self.out_mode == OUT_LSCRS else 2
         if out is None:
             out = torch.empty((n_out, tracks, seg_len), dtype=torch.float32, device=L.device)
-        elif out.shape != (n_out, tracks, seg_len) or not out.is_contiguous() or out.dtype != torch.float32:
-            raise ValueError(f"out must be a contiguous float32 tensor of shape {(n_out, tracks, seg_len)}")
+        elif (out.shape != (n_out, tracks, seg_len) or out.dtype != torch.float32 or
+              not all(out[i].is_contiguous() for i in range(n_out))):
+            raise ValueError(f"out must be a float32 tensor of shape {(n_out, tracks, seg_len)} with contiguous channels")
         oc, ol, orr = (out[0], out[1], out[2]) if n_out == 3 else (None, out[0], out[1])
         if seg_len == 0:
             return tuple(o[0] for o in out) if squeeze else tuple(out[i] for i in range(n_out))
@@ -319,12 +320,16 @@ class Plan:
         """Free the device buffers and pinned staging the host-buffer calls cache in the plan."""
         _check(self._lib.upmix_plan_release_host(self._h))
 
-    def _host_call(self, lp: int, rp: int, dtype: int, sl: int, sr: int, n: int, n_threads: int = 0):
-        """Runs the host pipeline into FRESH pinned output tensors (torch's caching host allocator hands back
-        blocks of results that have been dropped, never one that is still referenced)."""
+    def _host_call(self, lp: int, rp: int, dtype: int, sl: int, sr: int, n: int, n_threads: int = 0, pinned_out: bool = True):
+        """Runs the host pipeline into FRESH outputs: pinned tensors (torch's caching host allocator hands back blocks
+        of results that have been dropped, never one that is still referenced; a first-time block costs ~0.6 s per
+        GB to pin) or plain pageable memory (filled by the library's copy-out workers)."""
         torch = _torch()
         n_out = 3 if self.out_mode == OUT_LSCRS else 2
-        out = torch.empty((n_out, n), dtype=torch.float32, pin_memory=True)
+        if pinned_out:
+            out = torch.empty((n_out, n), dtype=torch.float32, pin_memory=True)
+        else:
+            out = torch.from_numpy(np.empty((n_out, n), dtype=np.float32))
         ptrs = [out[i].data_ptr() for i in range(n_out)]
         if n_out == 2:
             ptrs = [None] + ptrs
@@ -348,9 +353,12 @@ class Plan:
                               n_threads)
         return tuple(out[i] for i in range(n_out))
 
-    def process_host(self, L: np.ndarray, R: np.ndarray, n_threads: int = 0):
+    def process_host(self, L: np.ndarray, R: np.ndarray, n_threads: int = 0, pinned_out: Optional[bool] = None):
         """numpy in (float32 or float64, any positive stride -- e.g. the two columns of the interleaved float64
-        array sf.read returns, main.py:43-50), fresh float32 numpy arrays out (views of pinned memory)."""
+        array sf.read returns, main.py:43-50), fresh float32 numpy arrays out, like the reference's (CE:503-513).
+        pinned_out: None = UPMIX_NUMPY_PINNED_OUT (default 0: plain pageable arrays)."""
+        if pinned_out is None:
+            pinned_out = os.environ.get("UPMIX_NUMPY_PINNED_OUT", "0") not in ("", "0")
         _torch()
         L, R = np.asarray(L), np.asarray(R)
         if L.ndim != 1 or L.shape != R.shape:
@@ -365,7 +373,7 @@ class Plan:
         if n == 0:
             return tuple(np.zeros(0, dtype=np.float32) for _ in range(n_out))
         out = self._host_call(L.ctypes.data, R.ctypes.data, 0 if L.dtype == np.float32 else 1, L.strides[0] // item,
-                              R.strides[0] // item, n, n_threads)
+                              R.strides[0] // item, n, n_threads, pinned_out)
         return tuple(out[i].numpy() for i in range(n_out))
 
 

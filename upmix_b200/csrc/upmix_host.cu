@@ -18,6 +18,7 @@
 #include "../../include/upmix_b200.h"
 
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -167,7 +168,10 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
 
     if (n_threads <= 0) {
         const char* ev = getenv("UPMIX_HOST_THREADS");
-        n_threads = ev ? atoi(ev) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        // default: the cores of the box divided by the ranks sharing it (torchrun's LOCAL_WORLD_SIZE), at most 16
+        const char* lw = getenv("LOCAL_WORLD_SIZE");
+        const unsigned ranks = lw && atoi(lw) > 0 ? (unsigned)atoi(lw) : 1u;
+        n_threads = ev ? atoi(ev) : (int)std::min(16u, std::max(2u, std::thread::hardware_concurrency() / ranks));
         n_threads = std::max(1, std::min(n_threads, 32));
     }
     const bool in_direct = dtype == UPMIX_F32 && stride_l == 1 && stride_r == 1 && is_pinned(L) && is_pinned(R);
@@ -244,14 +248,15 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
         HOST_CHECK(cudaStreamCreateWithFlags(&c.s_main, cudaStreamNonBlocking));
         HOST_CHECK(cudaStreamCreateWithFlags(&c.s_down, cudaStreamNonBlocking));
     }
-    const size_t n_events = (size_t)n_chunks + n_segs + n_pieces;
+    const int n_up = std::max(n_chunks, n_segs);              // ev_up: per chunk (staged input) or per segment (pinned input)
+    const size_t n_events = (size_t)n_up + n_segs + n_pieces;
     while (c.events.size() < n_events) {
         cudaEvent_t e;
         HOST_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c.events.push_back(e);
     }
     cudaEvent_t* ev_up = c.events.data();
-    cudaEvent_t* ev_comp = ev_up + n_chunks;
+    cudaEvent_t* ev_comp = ev_up + n_up;
     cudaEvent_t* ev_down = ev_comp + n_segs;
 
     std::vector<std::atomic<int>> up_rec(n_chunks), down_rec(n_pieces), out_done(n_pieces);
@@ -269,6 +274,11 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
     // ---- input side ----
     const bool paired = !in_direct && stride_l == 2 && stride_r == 2 &&
                         (const char*)R == (const char*)L + (dtype == UPMIX_F64 ? 8 : 4);
+    static const bool trace = [] { const char* e = getenv("UPMIX_HOST_TRACE"); return e && atoi(e) != 0; }();
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto t_start = clk::now();
+    std::vector<double> t_gather(64, 0.0), t_wait(64, 0.0), t_copyout(64, 0.0);
     auto upload_worker = [&](int w, int n_workers) {
         cudaSetDevice(plan->device);
         for (int ck = w; ck < n_chunks; ck += n_workers) {
@@ -276,7 +286,9 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
             const int64_t a = (int64_t)ck * chunk, len = std::min(chunk, n - a);
             const int slot = ck % c.ns_in;
             // the slot's previous chunk (ck - ns_in) was this worker's: its copy must have left the slot
+            const auto t0 = clk::now();
             if (ck >= c.ns_in && cudaEventSynchronize(ev_up[ck - c.ns_in]) != cudaSuccess) { err.store(1); return; }
+            const auto t1 = clk::now();
             float* sl = c.pin_in + (int64_t)slot * 2 * slot_len;
             float* sr = sl + slot_len;
             if (dtype == UPMIX_F64) {
@@ -292,6 +304,9 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
                     gather_chunk((const float*)R + a * stride_r, stride_r, len, sr);
                 }
             }
+            const auto t2 = clk::now();
+            t_wait[w & 63] += secs(t0, t1);
+            t_gather[w & 63] += secs(t1, t2);
             cudaError_t e = cudaMemcpyAsync(d_l + a, sl, (size_t)len * sizeof(float), cudaMemcpyHostToDevice, c.s_up);
             if (e == cudaSuccess) e = cudaMemcpyAsync(d_r + a, sr, (size_t)len * sizeof(float), cudaMemcpyHostToDevice, c.s_up);
             if (e == cudaSuccess) e = cudaEventRecord(ev_up[ck], c.s_up);
@@ -306,22 +321,17 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
             if (!wait_flag(down_rec[p], err)) return;
             if (cudaEventSynchronize(ev_down[p]) != cudaSuccess) { err.store(1); return; }
             const float* slot = c.pin_out + (int64_t)(p % c.ns_out) * 3 * slot_len;
+            const auto t0 = clk::now();
             for (int ch = ch0; ch < 3; ch++)
                 memcpy(h_o[ch] + pieces[p].a, slot + (int64_t)ch * slot_len, (size_t)pieces[p].len * sizeof(float));
+            t_copyout[w & 63] += secs(t0, clk::now());
             out_done[p].store(1, std::memory_order_release);
         }
     };
 
     std::vector<std::thread> threads;
     if (in_direct) {
-        for (int ck = 0; ck < n_chunks && !err.load(); ck++) {
-            const int64_t a = (int64_t)ck * chunk, len = std::min(chunk, n - a);
-            cudaError_t e = cudaMemcpyAsync(d_l + a, (const float*)L + a, (size_t)len * sizeof(float), cudaMemcpyHostToDevice, c.s_up);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(d_r + a, (const float*)R + a, (size_t)len * sizeof(float), cudaMemcpyHostToDevice, c.s_up);
-            if (e == cudaSuccess) e = cudaEventRecord(ev_up[ck], c.s_up);
-            if (e != cudaSuccess) err.store(1);
-            up_rec[ck].store(1, std::memory_order_release);
-        }
+        // pinned float32 input: uploaded in place, one copy per channel for what each segment adds (see the segment loop)
     } else {
         const int nw = std::min(n_threads, n_chunks);
         for (int w = 0; w < nw; w++) threads.emplace_back(upload_worker, w, nw);
@@ -334,12 +344,26 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
     // ---- caller thread: segments ----
     int rc = UPMIX_OK;
     int next_chunk = 0, next_piece = 0;
+    int64_t uploaded = 0;
     for (int i = 0; i < n_segs && rc == UPMIX_OK && !err.load(); i++) {
         const int64_t a = bounds[i], b = bounds[i + 1];
-        const int last = (int)((std::min(n, b + plan->halo) - 1) / chunk);
-        for (; next_chunk <= last; next_chunk++) {
-            if (!wait_flag(up_rec[next_chunk], err)) break;
-            if (cudaStreamWaitEvent(c.s_main, ev_up[next_chunk], 0) != cudaSuccess) err.store(1);
+        const int64_t need = std::min(n, b + plan->halo);
+        if (in_direct) {
+            if (uploaded < need) {
+                const size_t bytes = (size_t)(need - uploaded) * sizeof(float);
+                cudaError_t e = cudaMemcpyAsync(d_l + uploaded, (const float*)L + uploaded, bytes, cudaMemcpyHostToDevice, c.s_up);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(d_r + uploaded, (const float*)R + uploaded, bytes, cudaMemcpyHostToDevice, c.s_up);
+                if (e == cudaSuccess) e = cudaEventRecord(ev_up[i], c.s_up);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(c.s_main, ev_up[i], 0);
+                if (e != cudaSuccess) { err.store(1); break; }
+                uploaded = need;
+            }
+        } else {
+            const int last = (int)((need - 1) / chunk);
+            for (; next_chunk <= last; next_chunk++) {
+                if (!wait_flag(up_rec[next_chunk], err)) break;
+                if (cudaStreamWaitEvent(c.s_main, ev_up[next_chunk], 0) != cudaSuccess) err.store(1);
+            }
         }
         if (err.load()) break;
         rc = upmix_process_segment(plan, d_l, d_r, 0, n, n, a, b, 1, c.cap, d_o[0] ? d_o[0] + a : nullptr, d_o[1] + a, d_o[2] + a,
@@ -349,13 +373,17 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
             err.store(1);
             break;
         }
+        if (out_direct) {                                     // pinned outputs: one copy per channel and segment, in place
+            cudaError_t e = cudaSuccess;
+            for (int ch = ch0; ch < 3 && e == cudaSuccess; ch++)
+                e = cudaMemcpyAsync(h_o[ch] + a, d_o[ch] + a, (size_t)(b - a) * sizeof(float), cudaMemcpyDeviceToHost, c.s_down);
+            if (e != cudaSuccess) { err.store(1); break; }
+            continue;
+        }
         for (; next_piece < n_pieces && pieces[next_piece].seg == i; next_piece++) {
             const Piece& pc = pieces[next_piece];
             cudaError_t e = cudaSuccess;
-            if (out_direct) {
-                for (int ch = ch0; ch < 3 && e == cudaSuccess; ch++)
-                    e = cudaMemcpyAsync(h_o[ch] + pc.a, d_o[ch] + pc.a, (size_t)pc.len * sizeof(float), cudaMemcpyDeviceToHost, c.s_down);
-            } else {
+            {
                 // the slot's previous piece must have been copied out to the caller's arrays
                 if (next_piece >= c.ns_out && !wait_flag(out_done[next_piece - c.ns_out], err)) break;
                 float* slot = c.pin_out + (int64_t)(next_piece % c.ns_out) * 3 * slot_len;
@@ -368,8 +396,18 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
         }
     }
     if (rc != UPMIX_OK || err.load()) err.store(1);          // release every waiter
+    const auto t_launched = clk::now();
     for (std::thread& t : threads) t.join();
+    const auto t_joined = clk::now();
     const cudaError_t e_up = cudaStreamSynchronize(c.s_up), e_main = cudaStreamSynchronize(c.s_main), e_down = cudaStreamSynchronize(c.s_down);
+    if (trace) {
+        double g = 0, wt = 0, co = 0;
+        for (int i = 0; i < 64; i++) { g += t_gather[i]; wt += t_wait[i]; co += t_copyout[i]; }
+        fprintf(stderr, "[upmix host] n=%lld threads=%d in_direct=%d out_direct=%d chunks=%d segs=%d: setup+launch %.1f ms, join %.1f ms, drain %.1f ms; "
+                        "workers: gather %.1f ms, slot wait %.1f ms, copy-out %.1f ms (summed over threads)\n",
+                (long long)n, n_threads, (int)in_direct, (int)out_direct, n_chunks, n_segs, 1e3 * secs(t_start, t_launched),
+                1e3 * secs(t_launched, t_joined), 1e3 * secs(t_joined, clk::now()), 1e3 * g, 1e3 * wt, 1e3 * co);
+    }
     if (rc != UPMIX_OK) return rc;
     if (err.load() || e_up != cudaSuccess || e_main != cudaSuccess || e_down != cudaSuccess) {
         const cudaError_t e = e_up != cudaSuccess ? e_up : e_main != cudaSuccess ? e_main : e_down != cudaSuccess ? e_down : cudaGetLastError();
