@@ -728,3 +728,158 @@ def test_large_batch_goes_through_in_track_groups(ce):
                     assert torch.equal(bch[t], sch), (t, direct_min)
         finally:
             os.environ.pop("UPMIX_DIRECT_MIN", None)
+
+
+# ---------------------------------------------------------------------------------------------------
+# decimated path (upmix_dec.cu): eligibility boundaries, every (P, Q) family, waves, merged bands, fold-down
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_fft,top_bin", [(2048, 5), (2048, 127), (2048, 128), (4096, 255), (4096, 256), (8192, 127),
+                                           (8192, 128), (8192, 511), (8192, 512), (16384, 255), (16384, 256),
+                                           (32768, 300), (65536, 127), (65536, 256), (65536, 511), (65536, 512)])
+def test_decimated_band_boundaries(ce, n_fft, top_bin):
+    """Both sides of the decimated kernels' eligibility rule (every live bin below P = 128 / 256 / 512 <= n_fft/16):
+    hard-zero pass band [3, top_bin], so the last live bin is exactly top_bin; compared with the oracle, and with the
+    full-size kernels of a plan made with PLAN_NO_DECIMATE."""
+    import torch
+    from upmix_b200 import _native
+    sr = 48000
+    df = sr / n_fft
+    f_low, f_high = 3 * df, top_bin * df
+    e = ce.MultiBandExtractorAccu(n_fft, 0.75, ce.make_blackman_harris, f_low, f_high, sr, "hard_zero", 0.0, 0.0)
+    b = uo.make_band(n_fft, 0.75, uo.blackman_harris, f_low, f_high, sr, "hard_zero", 0.0, 0.0)
+    assert int(np.nonzero(e.band_gain())[0].max()) == top_bin
+    n = 2 * n_fft + 4321
+    L, R = uo.synth_stereo(n, 200 + top_bin, stress=True)
+    ref = uo.process_band_batched(b, L.astype(np.float64), R.astype(np.float64))
+    got = e.process_all_blocks(L, R)
+    peak = float(max(np.abs(L).max(), np.abs(R).max()))
+    assert_parity(ref, got, peak, what=f"N={n_fft} top_bin={top_bin}")
+    dl, dr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    full = ce.plan_for([e], _native.OUT_LSCRS, _native.PLAN_NO_DECIMATE).process(dl, dr)
+    for g, f in zip(got, full):
+        assert float(np.max(np.abs(g - f.cpu().numpy()))) < 2e-7
+
+
+def test_decimated_waves_tracks_and_modes_are_consistent(ce, monkeypatch):
+    """The decimated kernels under every scheduling the library uses: a scratch cap that forces waves of hops and
+    groups of tracks == one wave (bit for bit); accumulating == storing + staged band sum (bit for bit); merged
+    bands and the fold-down against the oracle."""
+    import torch
+    sr = 48000
+    edges = [0, 30, 120, 480, 1920, 7680]                       # two 65536-point bands (merged), 16384, 4096: all decimated
+    ext = quiet(ce.chain_bands, edges, 0.75, ce.make_blackman_harris, sr, "raised_cosine")
+    bands = uo.chain(edges, 0.75, uo.blackman_harris, sr)
+    n = 6 * sr + 1234
+    tracks = [uo.synth_stereo(n, 300 + t, stress=(t == 0)) for t in range(3)]
+    Ls = torch.from_numpy(np.stack([t[0] for t in tracks])).cuda()
+    Rs = torch.from_numpy(np.stack([t[1] for t in tracks])).cuda()
+    base = [o.clone() for o in ce.extract_center_left_right_multi_band_in_memory(Ls, Rs, sr, ext)]
+    ref = uo.upmix_multiband(bands, tracks[0][0].astype(np.float64), tracks[0][1].astype(np.float64))
+    assert_parity(ref, [o[0].cpu().numpy() for o in base], 0.5, what="6 bands, decimated")
+    from upmix_b200 import _native
+    from upmix_b200.center_extraction import _PLAN_CACHE
+    for env in ({"UPMIX_DEC_WS_MB": "1"}, {"UPMIX_DIRECT_MIN": "1"}, {"UPMIX_DIRECT_MIN": "1", "UPMIX_DEC_WS_MB": "1"},
+                {"UPMIX_DIRECT_MIN": str(1 << 40)}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got = ce.extract_center_left_right_multi_band_in_memory(Ls, Rs, sr, ext)
+        for a, b in zip(base, got):
+            assert torch.equal(a, b), env
+        for k in env:
+            monkeypatch.delenv(k)
+    # fold-down (centre folded per bin by the mask kernel) against Ls + 0.5 C / Rs + 0.5 C
+    fl, fr = ce.extract_stereo_fold_down(Ls[0].contiguous(), Rs[0].contiguous(), sr, ext)
+    want_l, want_r = ref[1].astype(np.float64) + 0.5 * ref[0], ref[2].astype(np.float64) + 0.5 * ref[0]
+    assert_parity((want_l, want_r), (fl.cpu().numpy(), fr.cpu().numpy()), 0.5, names=("outL", "outR"), what="fold-down, decimated")
+
+
+def test_cfg5_sampled_tracks_against_oracle(ce):
+    """BASELINE configs[4] at its stated track length: four of the 512 five-minute tracks (seeds 1000 + i), main.py's
+    default six bands, processed together as one wave of a batch; parity on windows at the start, an interior cut and
+    the end of each track."""
+    import torch
+    sr = 48000
+    edges = [0, 30, 120, 480, 1920, 7680]
+    ext = quiet(ce.chain_bands, edges, 0.75, ce.make_blackman_harris, sr, "raised_cosine")
+    bands = uo.chain(edges, 0.75, uo.blackman_harris, sr)
+    n = 300 * sr
+    picks = [0, 137, 300, 511]
+    sig = [uo.synth_stereo(n, 1000 + i) for i in picks]
+    Ls = torch.from_numpy(np.stack([s[0] for s in sig])).cuda()
+    Rs = torch.from_numpy(np.stack([s[1] for s in sig])).cuda()
+    out = [o.cpu().numpy() for o in ce.extract_center_left_right_multi_band_in_memory(Ls, Rs, sr, ext)]
+    margin = 65536
+    for t, (L, R) in enumerate(sig):
+        for a, b in ((0, 2 * sr), (n // 2 - sr // 2, n // 2 + sr // 2), (n - 2 * sr, n)):
+            lo, hi = max(0, a - margin), min(n, b + margin)
+            lo -= lo % 16384
+            ref = uo.upmix_multiband(bands, L[lo:hi].astype(np.float64), R[lo:hi].astype(np.float64))
+            ia = a if lo == 0 else max(a, lo + 49152)
+            ib = b if hi == n else min(b, hi - 65536)
+            assert_parity([x[ia - lo:ib - lo] for x in ref], [x[t, ia:ib] for x in out], 0.5, what=f"track {picks[t]} [{a},{b})")
+
+
+def test_random_crossovers_on_device(ce):
+    """Seeded random crossover sets, both crossover modes, 44.1 / 48 / 96 kHz (the GPU twin of
+    tests/test_oracle.py::test_live_against_reference_random_crossovers, which pins the oracle to the live reference)."""
+    rng = np.random.default_rng(11)
+    for trial in range(5):
+        sr = int(rng.choice([44100, 48000, 96000]))
+        edges = [0.0] + sorted(float(x) for x in rng.uniform(60, 9000, size=int(rng.integers(1, 5))))
+        mode = ["raised_cosine", "hard_zero"][trial % 2]
+        max_block = int(rng.choice([8192, 16384, 65536]))
+        ext = quiet(ce.chain_bands, edges, 0.75, ce.make_blackman_harris, sr, mode, max_block_size=max_block)
+        bands = uo.chain(edges, 0.75, uo.blackman_harris, sr, mode=mode, max_block=max_block)
+        assert [e.block_size for e in ext] == [b.n_fft for b in bands]
+        L, R = uo.synth_stereo(3 * max_block + 20011, 100 + trial, sr=sr, stress=True)
+        ref = uo.upmix_multiband(bands, L.astype(np.float64), R.astype(np.float64))
+        got = ce.extract_center_left_right_multi_band_in_memory(L, R, sr, ext)
+        rep = assert_parity(ref, got, float(max(np.abs(L).max(), np.abs(R).max())), what=f"trial {trial}: sr={sr} edges={edges} {mode}")
+        print(trial, sr, [e.block_size for e in ext], mode, [(nm, round(s, 1)) for nm, s, _ in rep])
+
+
+def test_near_silence_and_digital_zero(ce):
+    """Segments at 1e-9 and 1e-12 of full scale and exact zeros: the centre factor's m/(m+EPS) regime and the
+    flush-to-zero square root / reciprocal of the mask (fft_device.cuh: sqrt_approx / rcp_approx)."""
+    sr = 48000
+    edges = [0, 200, 2000]
+    ext = quiet(ce.chain_bands, edges, 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=16384)
+    bands = uo.chain(edges, 0.75, uo.blackman_harris, sr, max_block=16384)
+    n = 5 * sr
+    L, R = uo.synth_stereo(n, 77)
+    s = sr
+    L[s:2 * s] *= np.float32(1e-9)
+    R[s:2 * s] *= np.float32(1e-9)
+    L[2 * s:3 * s] *= np.float32(1e-12)
+    R[2 * s:3 * s] *= np.float32(1e-12)
+    L[3 * s:4 * s] = 0.0
+    R[3 * s:4 * s] = 0.0
+    ref = uo.upmix_multiband(bands, L.astype(np.float64), R.astype(np.float64))
+    got = ce.extract_center_left_right_multi_band_in_memory(L, R, sr, ext)
+    assert_parity(ref, got, 0.5, what="near-silence")
+    # inside the quiet segments the error is judged against the quiet signal itself
+    for a, scale in ((s + 16384, 1e-9), (2 * s + 16384, 1e-12)):      # frames that lie wholly inside the quiet second
+        b = a + s - 2 * 16384
+        for r_, g_ in zip(ref, got):
+            assert float(np.max(np.abs(r_[a:b] - g_[a:b]))) <= 1e-4 * scale
+    # an all-zero input gives exact zeros
+    z = np.zeros(2 * sr, np.float32)
+    for o in ce.extract_center_left_right_multi_band_in_memory(z, z, sr, ext):
+        assert not np.any(o)
+
+
+def test_plan_follows_in_place_edits_of_the_windows(ce):
+    """The reference's analysis_window / synthesis_window are plain arrays (CE:257-258): editing them in place must
+    rebuild the device tables, not reuse a stale plan."""
+    sr = 48000
+    e = ce.MultiBandExtractorAccu(1024, 0.75, ce.make_blackman_harris, 500.0, 4000.0, sr, "raised_cosine", 100.0, 500.0)
+    L, R = uo.synth_stereo(20000, 8)
+    first = e.process_all_blocks(L, R)
+    e.synthesis_window[:] *= np.float32(0.5)
+    second = e.process_all_blocks(L, R)
+    assert np.allclose(second[0], 0.5 * first[0], atol=1e-7) and not np.array_equal(second[0], first[0])
+    ext = [e]
+    third = ce.extract_center_left_right_multi_band_in_memory(L, R, sr, ext)
+    e.analysis_window[:] *= np.float32(2.0)
+    fourth = ce.extract_center_left_right_multi_band_in_memory(L, R, sr, ext)
+    assert np.array_equal(third[0], second[0]) and not np.array_equal(fourth[0], third[0])

@@ -91,7 +91,8 @@ struct DecLayout {
 };
 
 DecLayout make_dec_layout(const BandDev& b, int64_t seg_len, int n_tracks) {
-    static const int64_t cap = [] { const char* e = getenv("UPMIX_DEC_WS_MB"); return (int64_t)(e ? std::max(1, atoi(e)) : 1024) << 20; }();
+    const char* ev = getenv("UPMIX_DEC_WS_MB");               // read per call: tests force small waves with it
+    const int64_t cap = (int64_t)(ev ? std::max(1, atoi(ev)) : 1024) << 20;
     DecLayout d;
     const int64_t groups = b.dec.Q / 16;
     const int64_t per_frame = ((groups > 1 ? groups * 2 : 0) + 3) * (int64_t)b.dec.KP * (int64_t)sizeof(float2);
