@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
     constexpr int NST = CM == DEC_C16 ? 2 : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* buf = reinterpret_cast<float2*>(smem_raw);           // [P][DEC_QS]
+    float* prevbuf = reinterpret_cast<float*>(buf + P * DEC_QS);  // ACCUM: [2 regions][P/4 rows][16] previous sums of the hop
+    constexpr int RSZ = (P / 4) * 16;
     const int tid = threadIdx.x, q = tid & 15, jb = tid >> 4;
     const int g = blockIdx.y, track = blockIdx.z;
     const int K = b.dec.K, KP = b.dec.KP;
@@ -256,6 +258,38 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
             any = any || valid[s];
         }
         if (!any) continue;                                      // CTA-uniform: nothing has been accumulated yet
+
+        // ACCUM (this band adds to what the outputs hold: the bands before it, in band order): the hop this frame
+        // finishes is copied asynchronously (cp.async, no registers) from the outputs into shared memory now and read
+        // there by the last pass -- loaded at the store, the dependent HBM round trips cost 25 % of the kernel.  Two
+        // regions of P/4 rows x 16 floats: Ls / Rs rows of the tile (DEC_Y), the two 16-sequence halves (DEC_C32), the two
+        // runs (DEC_C16).  Hops cut by a segment edge, or not 16-byte aligned, take the plain loads below.
+        bool staged_prev = false;
+        if constexpr (ACCUM) {
+            const float* gsrc[2];
+            bool ok = true;
+#pragma unroll
+            for (int rg = 0; rg < 2; rg++) {
+                const int s = NST == 2 ? rg : 0;
+                const long long sb = fs[s] * H;
+                ok = ok && valid[s] && fs[s] >= h0s[s] && sb >= a.seg_begin && sb + H <= a.seg_end;
+                const float* base = (CM == DEC_Y ? (rg ? a.out_r : a.out_l) : a.out_c) + (long long)track * a.out_stride + (sb - a.out_begin);
+                gsrc[rg] = base + (CM == DEC_Y ? 16 * g : CM == DEC_C32 ? 32 * g + 16 * rg : 0);
+                ok = ok && (reinterpret_cast<uintptr_t>(gsrc[rg]) & 15) == 0;
+            }
+            staged_prev = ok;
+            if (ok) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int c = tid + k * (P / 2);                 // 2 regions x P chunks of 16 bytes
+                    const int rg = c / P, row = (c % P) >> 2, c4 = c & 3;
+                    const float* src = gsrc[rg] + Q * row + 4 * c4;
+                    const uint32_t dst = smem_u32(prevbuf + rg * RSZ + row * 16 + 4 * c4);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+        }
 
         // ---- expansion: live bins -> U_q[s] for the tile's columns, written column-wise (lanes = slots) ----
         if constexpr (CM == DEC_Y) {
@@ -382,6 +416,9 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
                 for (int r = 0; r < R0; r++) dst[r * DEC_QS] = v[it][r];
             }
         }
+        if constexpr (ACCUM) {
+            if (staged_prev) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
         __syncthreads();
 
         // ---- inverse pass 1 (radix 16): output r of butterfly j is point p = j + r*R0 of the sequence, in hop r/4
@@ -402,7 +439,7 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
             // this band adds to what the outputs hold (the bands before it, in band order): those values are requested
             // first and wait in registers while the butterfly runs
             float2 prev[4];
-            if (ACCUM) {
+            if (ACCUM && !staged_prev) {
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
                     const int n1 = m1 + r * R0 * Q, n2 = m2 + r * R0 * Q;
@@ -426,6 +463,11 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
                 if (r < 4) {
                     const float2 tot = __ffma2_rn(u[r], ww, acc[it][r]);
                     const int n1 = m1 + r * R0 * Q, n2 = m2 + r * R0 * Q;
+                    if (ACCUM && staged_prev) {                       // row p = j + r*R0 of the staged hop
+                        const float* pb = prevbuf + (j + r * R0) * 16;
+                        prev[r] = CM == DEC_C16 ? make_float2(pb[sid * RSZ + (q & 7)], pb[sid * RSZ + 8 + (q & 7)])
+                                                : make_float2(pb[q], pb[RSZ + q]);
+                    }
                     if (n1 >= e_lo && n1 < e_hi) __stcs(d1 + n1, ACCUM ? prev[r].x + tot.x : tot.x);
                     if (n2 >= e_lo && n2 < e_hi) __stcs(d2 + n2, ACCUM ? prev[r].y + tot.y : tot.y);
                 }
