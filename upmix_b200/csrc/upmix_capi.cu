@@ -181,18 +181,25 @@ int pick_hops_per_run(const UpmixPlan* p, int n_fft, int64_t total_hops, int n_t
     }
 }
 
-// Hops per run of dec_inv_kernel (a run replays 3 frames): as above, with `ctas_per_run` CTAs sharing a run's hop range
-// (the groups of 16 sequences) -- or two runs sharing a CTA (ctas_per_run = 0: the centre of a 16-sequence band).
+// Hops per run of dec_inv_kernel.  A run replays the 3 frames before it, and `ctas_per_run` CTAs share a run's hop range
+// (the groups of 16 sequences; 0: two runs share a CTA -- the centre of a 16-sequence band).  The kernel's time is about
+// (waves of co-resident CTAs) x (frames per run), so the run length that minimises that product is taken: long runs for
+// an hour of audio (3 replayed frames in ~290), one or two hops per run for a few seconds of it (the GPU is not full
+// anyway and what counts is the length of the serial chain per CTA).
 int pick_dec_hops_per_run(const UpmixPlan* p, const BandDev& b, int64_t total_hops, int n_tracks, int ctas_per_run) {
-    static const int run_max = [] { const char* e = getenv("UPMIX_DEC_RUN_MAX"); return e ? std::max(8, atoi(e)) : 256; }();
-    const int64_t ctas = (int64_t)p->sm_count * (1024 / b.dec.P);
-    const int64_t slots = ctas_per_run ? std::max<int64_t>(1, ctas / ctas_per_run) : 2 * ctas;
-    const int64_t work = total_hops * n_tracks;
-    for (int64_t waves = 1;; waves++) {
-        const int64_t runs_per_track = std::max<int64_t>(1, waves * slots / n_tracks);
-        const int64_t r = (total_hops + runs_per_track - 1) / runs_per_track;
-        if (r <= run_max || waves * slots >= work) return (int)std::max<int64_t>(8, r);
+    static const int run_max = [] { const char* e = getenv("UPMIX_DEC_RUN_MAX"); return e ? std::max(1, atoi(e)) : 320; }();
+    const int64_t slots = (int64_t)p->sm_count * (1024 / b.dec.P);
+    int64_t best_r = 1, best_cost = INT64_MAX;
+    auto cost_of = [&](int64_t r) {
+        const int64_t runs = (total_hops + r - 1) / r;
+        const int64_t ctas = (ctas_per_run ? runs * ctas_per_run : (runs + 1) / 2) * n_tracks;
+        return ((ctas + slots - 1) / slots) * (r + 3);
+    };
+    for (int64_t r = 1; r <= std::min<int64_t>(run_max, total_hops); r++) {
+        const int64_t c = cost_of(r);
+        if (c < best_cost || (c == best_cost && r > best_r)) { best_cost = c; best_r = r; }      // ties: fewer, longer runs
     }
+    return (int)best_r;
 }
 
 // One decimated band over hops [a.hop_begin, a.hop_end) of every track, in waves: forward + mask of the wave's frames,
@@ -250,7 +257,8 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
     char* scratch = reinterpret_cast<char*>(workspace) + lay.band_out_bytes;
     const int nb = (int)p->bands.size();
     const cudaStream_t caller = st;
-    const bool fork = p->multi_stream && nb > 1 && band_state == nullptr && !direct;
+    // (block streaming forks too: every band has its own ring and its own output slot)
+    const bool fork = p->multi_stream && nb > 1 && !direct;
     bool first = true;
     bool used[UpmixPlan::N_AUX] = {false, false, false};
     int next_fused = 1;
@@ -605,6 +613,9 @@ int upmix_plan_create_ex(int n_bands, const UpmixBandDesc* bands, int out_mode, 
             ok = cudaStreamCreateWithFlags(&p->aux[si], cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreateWithFlags(&p->ev_join[si], cudaEventDisableTiming) == cudaSuccess;
         if (!ok) p->multi_stream = false;
+        const char* eg = getenv("UPMIX_GRAPHS");
+        p->use_graphs = !(eg && atoi(eg) == 0);
+        if (p->use_graphs && cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) != cudaSuccess) p->use_graphs = false;
     }
     e = cudaMemcpy(p->tables, host.data(), (size_t)floats * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -624,6 +635,8 @@ int upmix_plan_destroy(UpmixPlan* plan) {
         if (plan->ev_join[si]) cudaEventDestroy(plan->ev_join[si]);
     }
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    for (UpmixPlan::GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
+    if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
     upmix_host_ctx_destroy(plan->host);
     cudaFree(plan->tables);
     delete plan;
@@ -675,8 +688,57 @@ int upmix_process_segment(const UpmixPlan* plan, const float* L, const float* R,
                     (long long)(in_begin + in_len), (long long)need_lo, (long long)need_hi);
     DeviceGuard guard(plan->device);
     if (!guard.ok) return fail(UPMIX_E_CUDA, "cannot select device %d", plan->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // short calls: replay (or capture) a CUDA graph of exactly this call
+    UpmixPlan* mp = const_cast<UpmixPlan*>(plan);
+    if (mp->use_graphs && mp->cap_stream && !direct_sum(seg_end - seg_begin, n_tracks)) {
+        uint64_t key[16] = {(uint64_t)(uintptr_t)L, (uint64_t)(uintptr_t)R, (uint64_t)in_begin, (uint64_t)in_len, (uint64_t)n_total,
+                            (uint64_t)seg_begin, (uint64_t)seg_end, (uint64_t)n_tracks, (uint64_t)in_stride, (uint64_t)(uintptr_t)out_c,
+                            (uint64_t)(uintptr_t)out_l, (uint64_t)(uintptr_t)out_r, (uint64_t)out_stride, (uint64_t)(uintptr_t)workspace,
+                            (uint64_t)workspace_bytes, 0};
+        if (const char* ev = getenv("UPMIX_DIRECT_MIN")) key[15] = (uint64_t)atoll(ev);      // (tests flip the band-sum mode)
+        for (UpmixPlan::GraphEntry& g : mp->graphs)
+            if (memcmp(g.key, key, sizeof(key)) == 0) {
+                g.last_use = ++mp->graph_clock;
+                CU_CHECK(cudaGraphLaunch(g.exec, st));
+                launch_count_add(g.n_kernels);
+                return UPMIX_OK;
+            }
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        const bool caller_capturing = st && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+        if (!caller_capturing && cudaStreamBeginCapture(mp->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const unsigned long long before = launch_count(false);
+            const int rc2 = run_segment(plan, L, R, in_begin, in_begin + in_len, n_total, seg_begin, seg_end, n_tracks, in_stride, out_c,
+                                        out_l, out_r, out_stride, workspace, workspace_bytes, nullptr, mp->cap_stream);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ee = cudaStreamEndCapture(mp->cap_stream, &graph);
+            cudaGraphExec_t exec = nullptr;
+            if (rc2 == UPMIX_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                cudaGraphDestroy(graph);
+                UpmixPlan::GraphEntry g;
+                memcpy(g.key, key, sizeof(key));
+                g.exec = exec;
+                g.n_kernels = (int)(launch_count(false) - before);
+                g.last_use = ++mp->graph_clock;
+                if (mp->graphs.size() >= 16) {                  // evict the least recently used
+                    size_t lru = 0;
+                    for (size_t i = 1; i < mp->graphs.size(); i++)
+                        if (mp->graphs[i].last_use < mp->graphs[lru].last_use) lru = i;
+                    cudaGraphExecDestroy(mp->graphs[lru].exec);
+                    mp->graphs[lru] = g;
+                } else {
+                    mp->graphs.push_back(g);
+                }
+                CU_CHECK(cudaGraphLaunch(exec, st));
+                return UPMIX_OK;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();                                 // capture failed: run the call the plain way
+            if (rc2 != UPMIX_OK) return rc2;
+        }
+    }
     return run_segment(plan, L, R, in_begin, in_begin + in_len, n_total, seg_begin, seg_end, n_tracks, in_stride, out_c, out_l,
-                       out_r, out_stride, workspace, workspace_bytes, nullptr, reinterpret_cast<cudaStream_t>(stream));
+                       out_r, out_stride, workspace, workspace_bytes, nullptr, st);
 }
 
 int upmix_process(const UpmixPlan* plan, const float* L, const float* R, int64_t n_samples, int n_tracks,

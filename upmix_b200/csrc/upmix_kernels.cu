@@ -763,6 +763,7 @@ cudaError_t launch_fma_peak(float* out, int blocks, int iters, cudaStream_t st) 
 // ---------------------------------------------------------------------------------------------
 static unsigned long long g_launches = 0;
 unsigned long long& launch_counter() { return g_launches; }
+void launch_count_add(unsigned long long n) { g_launches += n; }     // kernels replayed by a CUDA graph
 unsigned long long launch_count(bool reset) {
     const unsigned long long v = g_launches;
     if (reset) g_launches = 0;

@@ -35,5 +35,6 @@ cudaError_t launch_fir(const float* x, long long n, int n_tracks, long long x_st
                        long long y_stride, cudaStream_t st);
 cudaError_t launch_fma_peak(float* out, int blocks, int iters, cudaStream_t st);
 unsigned long long launch_count(bool reset);
+void launch_count_add(unsigned long long n);
 
 }  // namespace upmix

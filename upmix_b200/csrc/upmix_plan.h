@@ -32,6 +32,18 @@ struct UpmixPlan {
     cudaEvent_t ev_join[N_AUX] = {nullptr, nullptr, nullptr};
     bool multi_stream = false;
     UpmixHostCtx* host = nullptr;   // buffers of upmix_process_host_ex, created on first use
+    // Short calls (the staged band sum: a few seconds of audio, 10-20 launches on four streams) are captured once into
+    // a CUDA graph per argument set and replayed: the launch gaps are most of such a call's time.
+    struct GraphEntry {
+        uint64_t key[16];
+        cudaGraphExec_t exec;
+        int n_kernels;
+        uint64_t last_use;
+    };
+    std::vector<GraphEntry> graphs;
+    cudaStream_t cap_stream = nullptr;
+    uint64_t graph_clock = 0;
+    bool use_graphs = true;
 };
 
 
