@@ -162,7 +162,8 @@ int upmix_export_mix(int mode, float scale, const float* c, const float* l, cons
 
 /* WAV edge (main.py:43-55, 119-153 read/write 16-bit PCM through soundfile): interleaved PCM16 stereo
  * [n][2] -> planar float32 L, R (x/32768) and *peak = max|x| (main.py:53); interleaved float32 stereo ->
- * PCM16 (clip, x32768, round to nearest even).  Workspace: upmix_peak_workspace_bytes(). */
+ * PCM16 (x 32767, round to nearest even, saturating: libsndfile's
+ * float -> PCM_16 scale when sf.write is handed float data).  Workspace: upmix_peak_workspace_bytes(). */
 int upmix_pcm16_to_planar(const int16_t* interleaved, int64_t n, float* l, float* r, float* peak, void* workspace,
                           int64_t workspace_bytes, void* stream);
 int upmix_stereo_to_pcm16(const float* interleaved, int64_t n, int16_t* out, void* stream);

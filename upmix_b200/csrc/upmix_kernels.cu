@@ -598,9 +598,13 @@ __global__ void __launch_bounds__(256) export_mix_kernel(const float* __restrict
     }
 }
 
-// WAV edge: interleaved 16-bit PCM stereo [n][2] -> planar float32 (x / 32768, soundfile's float view of
-// PCM_16), and interleaved float32 stereo -> 16-bit PCM (clip to [-1, 32767/32768], x 32768, round to
-// nearest even), so that only 4 bytes per stereo sample cross PCIe in each direction.
+// WAV edge: interleaved 16-bit PCM stereo [n][2] -> planar float32 (x / 32768: libsndfile's float view of PCM_16,
+// which is what sf.read returns, main.py:43), and interleaved float32 stereo -> 16-bit PCM as sf.write(float data)
+// stores it (main.py:119-153): x * 32767 rounded to nearest even -- libsndfile's float -> PCM_16 conversion scales by
+// 0x7FFF when it is not asked to clip (pcm.c f2s_array; soundfile is not installed here, so this is pinned from the
+// library's documented behaviour, not from a fixture).  Out-of-range values saturate here (libsndfile would wrap);
+// main.py scales its outputs to the input's peak (main.py:90-97), so they do not occur on that path.  4 bytes per
+// stereo sample cross PCIe in each direction.
 __global__ void __launch_bounds__(256) pcm16_to_planar_kernel(const short2* __restrict__ in, long long n, float* __restrict__ l,
                                                               float* __restrict__ r, float* __restrict__ peak_partial) {
     float m = 0.f;
@@ -634,8 +638,8 @@ __global__ void max_final_kernel(const float* __restrict__ partial, int n_blocks
 __global__ void __launch_bounds__(256) stereo_to_pcm16_kernel(const float2* __restrict__ in, long long n, short2* __restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float2 v = in[i];
-        const float a = fminf(fmaxf(v.x, -1.f), 32767.f / 32768.f) * 32768.f;
-        const float b = fminf(fmaxf(v.y, -1.f), 32767.f / 32768.f) * 32768.f;
+        const float a = fminf(fmaxf(v.x * 32767.f, -32768.f), 32767.f);
+        const float b = fminf(fmaxf(v.y * 32767.f, -32768.f), 32767.f);
         out[i] = make_short2((short)__float2int_rn(a), (short)__float2int_rn(b));
     }
 }

@@ -59,5 +59,6 @@ def write_wav(path: str, data: np.ndarray, sr: int) -> None:
     except ImportError:
         pass
     from scipy.io import wavfile
-    pcm = np.clip(np.asarray(data, dtype=np.float64), -1.0, 32767.0 / 32768.0)
-    wavfile.write(path, int(sr), np.round(pcm * 32768.0).astype(np.int16))
+    # libsndfile's float -> PCM_16 conversion (what sf.write does with float data): x * 0x7FFF, round to nearest even
+    pcm = np.clip(np.rint(np.asarray(data, dtype=np.float64) * 32767.0), -32768, 32767)
+    wavfile.write(path, int(sr), pcm.astype(np.int16))
