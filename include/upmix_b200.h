@@ -69,7 +69,12 @@ int upmix_plan_create(int n_bands, const UpmixBandDesc* bands, int out_mode, int
  * all but the top band of a crossover set) keep the full-size transform kernels instead of the decimated
  * ones; results agree to float32 rounding.  Block streaming always uses the full-size kernels, so a plan made
  * with this flag gives bit-identical results through upmix_process and upmix_stream_block. */
-enum { UPMIX_PLAN_NO_DECIMATE = 1 };
+enum {
+    UPMIX_PLAN_NO_DECIMATE = 1,
+    /* dense bands of 256 / 512 / 1024 points keep the one-frame-per-CTA kernel instead of the frame-batched one
+     * (16 frames per tile); results agree to float32 rounding.  Block streaming always runs the one-frame kernels. */
+    UPMIX_PLAN_NO_BATCH = 2
+};
 int upmix_plan_create_ex(int n_bands, const UpmixBandDesc* bands, int out_mode, int device, int flags, UpmixPlan** out);
 int upmix_plan_destroy(UpmixPlan* plan);
 int upmix_plan_n_bands(const UpmixPlan* plan);

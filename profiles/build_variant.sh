@@ -10,7 +10,7 @@ HDR=/tmp/var_$NAME.h
 for d in "$@"; do echo "$d" >> $HDR; done
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -include $HDR"
 mkdir -p ../../gpurun_variants /tmp/var_$NAME
-SRCS="upmix_kernels upmix_capi upmix_host upmix_dec upmix_dec_128 upmix_dec_256 upmix_dec_512 upmix_fused_64_512 upmix_fused_1024_2048 upmix_fused_4096 upmix_fused_8192"
+SRCS="upmix_kernels upmix_capi upmix_host upmix_fb upmix_dec upmix_dec_128 upmix_dec_256 upmix_dec_512 upmix_fused_64_512 upmix_fused_1024_2048 upmix_fused_4096 upmix_fused_8192"
 for s in $SRCS; do nvcc $FLAGS -c $s.cu -o /tmp/var_$NAME/$s.o & done
 wait
 nvcc $FLAGS -shared -o ../../gpurun_variants/lib_$NAME.so /tmp/var_$NAME/*.o

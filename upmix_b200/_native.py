@@ -18,6 +18,8 @@ LIB_PATH = os.environ.get("UPMIX_B200_LIB") or os.path.join(_HERE, "csrc", "libu
 OUT_LSCRS = 0
 OUT_FOLD = 1
 PLAN_NO_DECIMATE = 1      # upmix_plan_create_ex flag: band-limited bands keep the full-size transform kernels
+PLAN_NO_BATCH = 2         # dense 256/512/1024-point bands keep the one-frame-per-CTA kernel (the one block streaming runs)
+PLAN_STREAM_KERNELS = 3   # both: offline results bit-identical to block streaming
 
 FUSED_MAX_N = 8192
 LARGE_MAX_N = 65536

@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $UPMIX_EXTRA_FLAGS"
-SRCS="upmix_kernels upmix_capi upmix_host upmix_dec upmix_dec_128 upmix_dec_256 upmix_dec_512 upmix_fused_64_512 upmix_fused_1024_2048 upmix_fused_4096 upmix_fused_8192"
+SRCS="upmix_kernels upmix_capi upmix_host upmix_fb upmix_dec upmix_dec_128 upmix_dec_256 upmix_dec_512 upmix_fused_64_512 upmix_fused_1024_2048 upmix_fused_4096 upmix_fused_8192"
 pids=""
 for s in $SRCS; do
     $NVCC $FLAGS -c $s.cu -o $s.o &

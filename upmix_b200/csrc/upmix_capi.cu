@@ -322,6 +322,19 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
         if (dec) {
             const int rc = run_dec_band(p, b, a, n_tracks, dec_scratch, dlay, st);
             if (rc) return rc;
+        } else if (b.fb.tw_full && !a.state && !a.mix) {
+            // dense band of 256 / 512 / 1024 points: 16 frames per tile; a run of r hops costs ceil((r + 3) / 16) tiles
+            const int64_t slots = (int64_t)p->sm_count * fb_ctas_per_sm(b.n_fft);
+            int64_t best_k = 1, best_cost = INT64_MAX;
+            for (int64_t k = 1; k <= 64; k++) {
+                const int64_t r = 16 * k - 3, runs = (total_hops + r - 1) / r;
+                const int64_t cost = ((runs * n_tracks + slots - 1) / slots) * k;
+                if (cost < best_cost || (cost == best_cost && runs * n_tracks > slots / 2)) { best_cost = cost; best_k = k; }
+                if (runs == 1) break;
+            }
+            a.hops_per_run = (int)(16 * best_k - 3);
+            const int n_runs = (int)((total_hops + a.hops_per_run - 1) / a.hops_per_run);
+            CU_CHECK(launch_band_fb(b, a, n_runs, n_tracks, st));
         } else if (b.n_fft <= FUSED_MAX_N) {
             if (a.state) {
                 a.hops_per_run = (int)total_hops;              // the ring is carried: one CTA per track
@@ -437,6 +450,8 @@ int upmix_plan_create_ex(int n_bands, const UpmixBandDesc* bands, int out_mode, 
     // (75 % overlap) splits its frames into n_fft/P sequences of P points.  dec_p[g] = P, or 0.
     bool use_dec = !(flags & UPMIX_PLAN_NO_DECIMATE);
     if (const char* ev = getenv("UPMIX_DEC")) use_dec = use_dec && atoi(ev) != 0;
+    bool use_fb = !(flags & UPMIX_PLAN_NO_BATCH);
+    if (const char* ev = getenv("UPMIX_FB")) use_fb = use_fb && atoi(ev) != 0;
     std::vector<int> dec_p(groups.size(), 0), dec_k(groups.size(), 0);
     bool any_four_step = false;
     for (size_t gi = 0; gi < groups.size(); gi++) {
@@ -461,6 +476,11 @@ int upmix_plan_create_ex(int n_bands, const UpmixBandDesc* bands, int out_mode, 
         if (dec_p[gi]) {
             const int64_t kp = round_up(dec_k[gi] + 1, 32);
             floats += 2 * (dec_p[gi] / 16) * 16 + 2 * kp + 2 * (d.n_fft / dec_p[gi] / 16) * kp;
+        }
+        {
+            int ra = 0, rb = 0, ha = 0;
+            fb_plan(d.n_fft, &ra, &rb, &ha);
+            if (use_fb && ra && !dec_p[gi] && d.hop * 4 == d.n_fft) floats += round_up(2 * ra * rb, 64) + round_up(2 * ha * 16, 64);
         }
         if (d.n_fft > FUSED_MAX_N) {
             floats += 2LL * d.n_fft + round_up(2LL * fft_tw_size(row_plan(d.n_fft / COL_R)), 64);
@@ -533,6 +553,31 @@ int upmix_plan_create_ex(int n_bands, const UpmixBandDesc* bands, int out_mode, 
             off += 2 * (int64_t)(Q / 16) * KP;
         }
         if (d.n_fft > FUSED_MAX_N && !dec_p[gi]) four_step = true;
+        b.fb.tw_full = b.fb.tw_half = nullptr;
+        {
+            int ra = 0, rb = 0, ha = 0;
+            fb_plan(d.n_fft, &ra, &rb, &ha);
+            if (use_fb && ra && !dec_p[gi] && d.hop * 4 == d.n_fft) {
+                // frame-batched kernel (upmix_fb.cuh): second-pass twiddles [k][r] of the n_fft- and n_fft/2-point transforms
+                for (int k = 0; k < ra; k++)
+                    for (int r = 0; r < rb; r++) {
+                        const double ang = -2.0 * M_PI * (double)((r * k) % d.n_fft) / d.n_fft;
+                        host[off + 2 * (k * rb + r)] = (float)cos(ang);
+                        host[off + 2 * (k * rb + r) + 1] = (float)sin(ang);
+                    }
+                b.fb.tw_full = reinterpret_cast<const float2*>(dbase + off);
+                off += round_up(2 * ra * rb, 64);
+                const int mh = d.n_fft / 2;
+                for (int k = 0; k < ha; k++)
+                    for (int r = 0; r < 16; r++) {
+                        const double ang = -2.0 * M_PI * (double)((r * k) % mh) / mh;
+                        host[off + 2 * (k * 16 + r)] = (float)cos(ang);
+                        host[off + 2 * (k * 16 + r) + 1] = (float)sin(ang);
+                    }
+                b.fb.tw_half = reinterpret_cast<const float2*>(dbase + off);
+                off += round_up(2 * ha * 16, 64);
+            }
+        }
         b.n_fft = d.n_fft;
         b.hop = d.hop;
         b.tw_fft = b.tw_inv = b.tw_half = b.tw_pack = b.tw_col = nullptr;

@@ -24,6 +24,12 @@ struct DecDev {
     const float2* tw_base;     // [Q/16][KP] exp(-2 pi i 16 g k / n_fft): twiddle of the first sequence of group g
 };
 
+// Frame-batched kernel of a dense band of 256 / 512 / 1024 points (upmix_fb.cuh).  tw_full == nullptr: not used.
+struct FbDev {
+    const float2* tw_full;     // [RA][RB]  exp(-2 pi i r k / n_fft): second-pass twiddles of the n_fft-point transform
+    const float2* tw_half;     // [HA][16]  exp(-2 pi i r k / (n_fft/2)): second pass of the centre's n_fft/2-point transform
+};
+
 // Device tables of one band (all in global memory, read-only during processing).
 struct BandDev {
     int n_fft;
@@ -43,6 +49,7 @@ struct BandDev {
     const float2* tw_pack;     // [n_fft/2]     exp(-2*pi*i*k/n_fft) for the real-signal packing (fused path)
     const float2* tw_col;      // [16][n_fft/16] exp(-2*pi*i*k1*n2/n_fft), large path only
     DecDev dec;                // decimated path (dec.P == 0: not used)
+    FbDev fb;                  // frame-batched path (fb.tw_full == nullptr: not used)
 };
 
 // Where the samples are.  Global sample index s of a track lives at in[s - in_begin] for

@@ -16,6 +16,10 @@ cudaError_t launch_col_inv_ola(const BandDev& b, const SegArgs& a, const WaveArg
                                cudaStream_t st);
 cudaError_t launch_col_inv_frame(const BandDev& b, const WaveArgs& w, float* ring, float* out_c, float* out_l, float* out_r,
                                  long long out_stride, int n_tracks, cudaStream_t st);
+// frame-batched kernel of dense 256 / 512 / 1024-point bands (upmix_fb.cu)
+cudaError_t launch_band_fb(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st);
+void fb_plan(int n_fft, int* ra, int* rb, int* ha);
+int fb_ctas_per_sm(int n_fft);
 // decimated path (upmix_dec.cu): forward transform + mask of the wave's frames; inverse + overlap-add of a range of hops
 cudaError_t launch_dec_fwd(const BandDev& b, const SegArgs& a, const DecWave& w, int n_tracks, cudaStream_t st);
 cudaError_t launch_dec_inv(const BandDev& b, const SegArgs& a, const DecWave& w, int n_runs, int n_tracks, bool centre,
