@@ -154,15 +154,15 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
         // ---- forward pass 0 (radix RA): point idx of lane f is sample f*H + idx of the staged span, times ana[idx] ----
         {
             float2 v[ITA][RA];
+            const bool live = F0 + q >= 0;
 #pragma unroll
             for (int it = 0; it < ITA; it++) {
                 const int j = jb + it * JS;
 #pragma unroll
                 for (int r = 0; r < RA; r++) {
-                    constexpr int dummy = 0;
-                    (void)dummy;
                     const int row = q + (4 * r) / RA, col = j + NBA * (r % (RA / 4));
-                    const float wn = __ldg(ana + j + NBA * r);
+                    // (frames before the start of the track do not exist, center_extraction.py:448: they add nothing)
+                    const float wn = live ? __ldg(ana + j + NBA * r) : 0.f;
                     v[it][r] = cscale(make_float2(in_l[row * HS + col], in_r[row * HS + col]), wn);
                 }
             }
