@@ -108,7 +108,7 @@ def test_bela_mode_vs_compiled_reference_fixture(ce, golden_dir):
         assert max(np.max(np.abs(sl - ol)), np.max(np.abs(sr_ - orr))) < 1e-6
         from upmix_b200 import _native
         n = (len(L) // hw) * hw
-        plan = ce.plan_for(up.bands, _native.OUT_FOLD, _native.PLAN_NO_DECIMATE)
+        plan = ce.plan_for(up.bands, _native.OUT_FOLD, _native.PLAN_STREAM_KERNELS)
         fl, fr = ce._run_plan(plan, L[:n], R[:n])
         assert np.array_equal(sl[3 * hw:], fl[:n - 3 * hw]) and np.array_equal(sr_[3 * hw:], fr[:n - 3 * hw])
 
@@ -464,9 +464,11 @@ def test_fold_down_with_large_band_and_stream_multitrack(ce):
     c, l, r = ce.extract_center_left_right_multi_band_in_memory(L, R, sr, ext)
     fl, fr = ce.extract_stereo_fold_down(L, R, sr, ext)
     assert np.max(np.abs(fl - (l + 0.5 * c))) < 1e-6 and np.max(np.abs(fr - (r + 0.5 * c))) < 1e-6
-    # block streaming, two tracks at once == offline result delayed by stream.delay
+    # block streaming, two tracks at once == offline result delayed by stream.delay: bit for bit on a plan whose offline
+    # call runs the kernels block streaming runs (PLAN_STREAM_KERNELS), to float32 rounding on the default plan
+    from upmix_b200 import _native
     small = quiet(ce.chain_bands, [0, 1000, 6000], 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=2048)
-    plan = ce.plan_for(small)
+    plan = ce.plan_for(small, _native.OUT_LSCRS, _native.PLAN_STREAM_KERNELS)
     st = plan.stream_open(2)
     n = 2048 * 12
     A = torch.from_numpy(np.stack([uo.synth_stereo(n, 1)[0], uo.synth_stereo(n, 2)[0]])).cuda()
@@ -474,9 +476,11 @@ def test_fold_down_with_large_band_and_stream_multitrack(ce):
     off = plan.process(A, B)
     blocks = [st.block(A[:, i:i + 512].contiguous(), B[:, i:i + 512].contiguous()) for i in range(0, n, 512)]
     d = st.delay
+    dflt = ce.plan_for(small).process(A, B)
     for ch in range(3):
         got = torch.cat([b[ch] for b in blocks], dim=1)
         assert torch.equal(got[:, d:], off[ch][:, :n - d]) and not got[:, :d].any()
+        assert float((dflt[ch] - off[ch]).abs().max()) < 1e-6
 
 
 def test_pcm16_edge_kernels(ce):
@@ -882,3 +886,59 @@ def test_plan_follows_in_place_edits_of_the_windows(ce):
     e.analysis_window[:] *= np.float32(2.0)
     fourth = ce.extract_center_left_right_multi_band_in_memory(L, R, sr, ext)
     assert np.array_equal(third[0], second[0]) and not np.array_equal(fourth[0], third[0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# frame-batched kernel of dense bands (upmix_fb.cuh): 16 frames per tile, overlap-add across lanes
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_fft", [256, 512, 1024])
+def test_frame_batched_dense_band(ce, n_fft, monkeypatch):
+    """Dense band (pass band up to Nyquist) through the frame-batched kernel: against the oracle for lengths around the
+    tile boundaries (a run is 16 k - 3 hops), against the one-frame kernel, time shards and multi-track batches bit for
+    bit, accumulating == storing + staged sum, fold-down."""
+    import torch
+    from upmix_b200 import _native
+    monkeypatch.setenv("UPMIX_FB_MAX_N", "1024")                # (1024 points take the one-frame kernel by default)
+    sr = 48000
+    H = n_fft // 4
+    f_low = 32.0 * sr / n_fft
+    e = ce.MultiBandExtractorAccu(n_fft, 0.75, ce.make_blackman_harris, f_low, sr / 2, sr, "raised_cosine", f_low / 4, 0.0)
+    b = uo.make_band(n_fft, 0.75, uo.blackman_harris, f_low, sr / 2, sr, "raised_cosine", f_low / 4, 0.0)
+    for n in (H - 1, 13 * H, 13 * H + 1, 29 * H + 7, 100 * H + 321):
+        L, R = uo.synth_stereo(n, n_fft + n, stress=n > 4 * n_fft)
+        ref = uo.process_band_batched(b, L.astype(np.float64), R.astype(np.float64))
+        got = e.process_all_blocks(L, R)
+        assert_parity(ref, got, float(max(np.abs(L).max(), np.abs(R).max(), 1e-3)), what=f"N={n_fft} n={n}")
+    n = 300 * H + 77
+    L, R = uo.synth_stereo(n, 5, stress=True)
+    dl, dr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    plan = ce.plan_for([e])
+    whole = [t.clone() for t in plan.process(dl, dr)]
+    one = ce.plan_for([e], _native.OUT_LSCRS, _native.PLAN_NO_BATCH).process(dl, dr)
+    for w, o in zip(whole, one):
+        assert float((w - o).abs().max()) < 2e-7
+    halo = plan.halo
+    for a_, b_ in ((0, 37 * H), (37 * H, 37 * H + 5), (37 * H + 5, 200 * H + 3), (200 * H + 3, n)):
+        lo, hi = max(0, a_ - halo), min(n, b_ + halo)
+        seg = plan.process_segment(dl[lo:hi].contiguous(), dr[lo:hi].contiguous(), lo, n, a_, b_)
+        for w, s_ in zip(whole, seg):
+            assert torch.equal(w[a_:b_], s_), (a_, b_)
+    batch = plan.process(torch.stack([dl, dr, dl.flip(0)]), torch.stack([dr, dl, dr * 0.5]))
+    for w, bt in zip(whole, batch):
+        assert torch.equal(w, bt[0])
+    # two bands (the top one dense): the second pipeline accumulates onto the first one's output
+    ext = quiet(ce.chain_bands, [0, 32.0 * sr / n_fft], 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=4 * n_fft)
+    bands = uo.chain([0, 32.0 * sr / n_fft], 0.75, uo.blackman_harris, sr, max_block=4 * n_fft)
+    assert ext[-1].block_size == n_fft
+    ref = uo.upmix_multiband(bands, L.astype(np.float64), R.astype(np.float64))
+    monkeypatch.setenv("UPMIX_DIRECT_MIN", "1")
+    direct = [t.clone() for t in ce.extract_center_left_right_multi_band_in_memory(dl, dr, sr, ext)]
+    monkeypatch.setenv("UPMIX_DIRECT_MIN", str(1 << 40))
+    staged = ce.extract_center_left_right_multi_band_in_memory(dl, dr, sr, ext)
+    monkeypatch.delenv("UPMIX_DIRECT_MIN")
+    assert_parity(ref, [t.cpu().numpy() for t in direct], 0.5, what=f"2 bands, top N={n_fft}")
+    for d_, s_ in zip(direct, staged):
+        assert torch.equal(d_, s_)
+    fl, fr = ce.extract_stereo_fold_down(dl, dr, sr, ext)
+    assert_parity((ref[1].astype(np.float64) + 0.5 * ref[0], ref[2].astype(np.float64) + 0.5 * ref[0]),
+                  (fl.cpu().numpy(), fr.cpu().numpy()), 0.5, names=("outL", "outR"), what="fold-down")

@@ -1,4 +1,6 @@
 // band_fb_kernel instantiations and dispatch (see upmix_fb.cuh).
+#include <stdlib.h>
+
 #include "upmix_fb.cuh"
 #include "upmix_launch.h"
 
@@ -10,6 +12,12 @@ unsigned long long& launch_counter();
 // builds the twiddle tables from them); 0: size not served by the frame-batched kernel
 void fb_plan(int n_fft, int* ra, int* rb, int* ha) {
     *ra = *rb = *ha = 0;
+    // Measured on B200, ms per band-hour of a dense band, frame-batched / one frame per CTA: 256 points 3.90 / 5.66, 512
+    // 4.30 / 5.00, 1024 6.02 / 4.84 -- a 1024-point tile of 16 frames needs 209 KB of shared memory (one CTA of 512
+    // threads per SM, 128 registers, half of them idle in the centre's radix-32 pass), so 1024 points keep the one-frame
+    // kernel unless UPMIX_FB_MAX_N says otherwise.
+    static const int max_n = [] { const char* e = getenv("UPMIX_FB_MAX_N"); return e ? atoi(e) : 512; }();
+    if (n_fft > max_n) return;
     switch (n_fft) {
         case 256: *ra = FbCfg<256>::RA; *rb = FbCfg<256>::RB; *ha = FbCfg<256>::HA; break;
         case 512: *ra = FbCfg<512>::RA; *rb = FbCfg<512>::RB; *ha = FbCfg<512>::HA; break;

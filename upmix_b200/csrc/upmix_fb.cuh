@@ -40,15 +40,22 @@ template <int N> __host__ __device__ constexpr int fb_smem_bytes() {
     return (N * FB_QS + (N / 2) * FB_QS) * (int)sizeof(float2);
 }
 
-// twiddles of a second pass: w[r] = tw[k * R + r], r = 0..R-1 (16-byte loads)
-template <int R>
-__device__ __forceinline__ void fb_load_tw(const float2* __restrict__ tw, int k, float2 (&w)[R]) {
+// v[r] *= tw[k * R + r] (CONJ: its conjugate), r = 1..R-1: the twiddles of a second pass, eight at a time (16-byte
+// loads) so that they never hold more than 16 registers beside the butterfly's 2R
+template <int R, bool CONJ>
+__device__ __forceinline__ void fb_apply_tw(const float2* __restrict__ tw, int k, float2 (&v)[R]) {
     const float4* __restrict__ t4 = reinterpret_cast<const float4*>(tw + k * R);
 #pragma unroll
-    for (int m = 0; m < R / 2; m++) {
-        const float4 x = __ldg(t4 + m);
-        w[2 * m] = make_float2(x.x, x.y);
-        w[2 * m + 1] = make_float2(x.z, x.w);
+    for (int c = 0; c < R / 8; c++) {
+        float4 x[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) x[m] = __ldg(t4 + 4 * c + m);
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const int r = 8 * c + 2 * m;
+            if (r > 0) v[r] = cmul(v[r], make_float2(x[m].x, CONJ ? -x[m].y : x[m].y));
+            v[r + 1] = cmul(v[r + 1], make_float2(x[m].z, CONJ ? -x[m].w : x[m].w));
+        }
     }
 }
 
@@ -129,15 +136,18 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
         t3.x = __shfl_up_sync(FULL, x3.x, 3, 16); t3.y = __shfl_up_sync(FULL, x3.y, 3, 16);
         // lanes 0..2: the older frames are the previous tile's (carry: lane 0 holds (y13 + y14) + y15, lane 1 y14 + y15,
         // lane 2 y15, each the matching hop segment)
-        const float2 A = q >= 3 ? cadd(t3, t2) : q == 2 ? cadd(carry, t2) : carry;
-        const float2 B = q == 0 ? carry : cadd(A, t1);
+        // (selects, no branches: lane 2 adds carry + t2, lane 1 keeps the carry, lane 0 adds nothing but its own frame;
+        // adding an exact zero changes nothing)
+        const float2 zero = make_float2(0.f, 0.f);
+        const float2 A = cadd(q >= 3 ? t3 : carry, q >= 2 ? t2 : zero);
+        const float2 B = cadd(A, q >= 1 ? t1 : zero);
         const float2 sum = cadd(B, x0);
         // carry for the next tile: lane 13 (x3 + x2@14) + x1@15, lane 14 x3 + x2@15, lane 15 x3 -> lanes 0, 1, 2
         float2 d1, d2;
         d1.x = __shfl_down_sync(FULL, x2.x, 1, 16); d1.y = __shfl_down_sync(FULL, x2.y, 1, 16);
         d2.x = __shfl_down_sync(FULL, x1.x, 2, 16); d2.y = __shfl_down_sync(FULL, x1.y, 2, 16);
-        const float2 A2 = cadd(x3, d1);
-        const float2 v = q == 13 ? cadd(A2, d2) : q == 14 ? A2 : x3;
+        const float2 A2 = cadd(x3, q <= 14 ? d1 : zero);
+        const float2 v = cadd(A2, q == 13 ? d2 : zero);
         const int src = (q < 3 ? 13 + q : q);
         carry.x = __shfl_sync(FULL, v.x, src, 16);
         carry.y = __shfl_sync(FULL, v.y, src, 16);
@@ -190,10 +200,7 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
 #pragma unroll
             for (int it = 0; it < ITB; it++) {
                 const int j = jb + it * JS;
-                float2 tw[RB];
-                fb_load_tw<RB>(b.fb.tw_full, j, tw);
-#pragma unroll
-                for (int r = 1; r < RB; r++) v[it][r] = cmul(v[it][r], tw[r]);
+                fb_apply_tw<RB, false>(b.fb.tw_full, j, v[it]);
                 Dft<RB, -1>::run(v[it]);
                 float2* __restrict__ dst = buf + j * FB_QS + q;
 #pragma unroll
@@ -283,10 +290,7 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
 #pragma unroll
             for (int it = 0; it < ITB; it++) {
                 const int j = jb + it * JS;
-                float2 tw[RB];
-                fb_load_tw<RB>(b.fb.tw_full, j, tw);
-#pragma unroll
-                for (int r = 1; r < RB; r++) v[it][r] = cmul(v[it][r], cconj(tw[r]));
+                fb_apply_tw<RB, true>(b.fb.tw_full, j, v[it]);
                 Dft<RB, +1>::run(v[it]);
 #pragma unroll
                 for (int r = 0; r < RB; r++) v[it][r] = cscale(v[it][r], __ldg(syn + j + r * RA));
@@ -327,14 +331,12 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
             __syncthreads();
             {
                 constexpr int NBL = M / HB;                       // = HA: butterflies per sequence of the last pass
-                float2 v[HB], tw[HB];
+                float2 v[HB];
                 const int j = jb;                                 // T / 16 = N / 32 = M / 16 butterflies per sequence: one each
                 const float2* __restrict__ src = cbuf + j * FB_QS + q;
 #pragma unroll
                 for (int r = 0; r < HB; r++) v[r] = src[r * NBL * FB_QS];
-                fb_load_tw<HB>(b.fb.tw_half, j, tw);
-#pragma unroll
-                for (int r = 1; r < HB; r++) v[r] = cmul(v[r], cconj(tw[r]));
+                fb_apply_tw<HB, true>(b.fb.tw_half, j, v);
                 Dft<HB, +1>::run(v);
 #pragma unroll
                 for (int r = 0; r < HB; r++) {
@@ -364,7 +366,21 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
                     float* __restrict__ po = outp[ch] + (sb - a.out_begin);
                     const float* __restrict__ sg = stage + ch * 16 * HS;
                     const bool vec = (reinterpret_cast<uintptr_t>(po) & 7) == 0;      // CTA-uniform
-                    if (vec) {
+                    if (vec && e_lo == 0 && e_hi == 16 * H) {                           // the usual tile: every hop goes out whole
+                        float2 pv[(16 * H / 2) / T];
+                        if (ACCUM) {
+#pragma unroll
+                            for (int i = 0; i < (16 * H / 2) / T; i++) pv[i] = __ldcs(reinterpret_cast<const float2*>(po) + tid + i * T);
+                        }
+#pragma unroll
+                        for (int i = 0; i < (16 * H / 2) / T; i++) {
+                            const int e = 2 * (tid + i * T);
+                            const int f = e / H, m = e - f * H;
+                            float2 s = *reinterpret_cast<const float2*>(sg + f * HS + m);
+                            if (ACCUM) s = make_float2(pv[i].x + s.x, pv[i].y + s.y);
+                            __stcs(reinterpret_cast<float2*>(po) + tid + i * T, s);
+                        }
+                    } else if (vec) {
                         float2 pv[(16 * H / 2 + T - 1) / T];
                         if (ACCUM) {
 #pragma unroll
