@@ -36,8 +36,11 @@ template <> struct FbCfg<512>  { static constexpr int RA = 32, RB = 16, HA = 16,
 template <> struct FbCfg<256>  { static constexpr int RA = 16, RB = 16, HA = 8,  CTAS = 4; };
 
 template <int N> __host__ __device__ constexpr int fb_stage_stride() { return N / 4 + 2; }     // floats per staged hop row: 2f + m never collides
+// the 1024-point kernel (one CTA of 512 threads per SM: 128 registers) keeps the overlap-add carries of lanes 0..2 in
+// shared memory: [N/32 butterfly rows][3 lanes][8 + 4 outputs]
+template <int N> __host__ __device__ constexpr bool fb_carry_in_smem() { return N >= 1024; }
 template <int N> __host__ __device__ constexpr int fb_smem_bytes() {
-    return (N * FB_QS + (N / 2) * FB_QS) * (int)sizeof(float2);
+    return (N * FB_QS + (N / 2) * FB_QS + (fb_carry_in_smem<N>() ? (N / 32) * 3 * 12 : 0)) * (int)sizeof(float2);
 }
 
 // v[r] *= tw[k * R + r] (CONJ: its conjugate), r = 1..R-1: the twiddles of a second pass, eight at a time (16-byte
@@ -99,8 +102,10 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
         if (whole) {
             const float* __restrict__ pl = gl + (s0 - a.in_begin);
             const float* __restrict__ pr = gr + (s0 - a.in_begin);
-            for (int c = tid; c < IN_ROWS * (H / 2); c += T) {
-                const int row = c / (H / 2), col = 2 * (c - row * (H / 2));
+            // T = 2H threads, H/2 eight-byte chunks per row: a thread keeps its column and walks down four rows at a time
+            const int col = 2 * (tid & (H / 2 - 1));
+#pragma unroll
+            for (int row = tid / (H / 2); row < IN_ROWS; row += 4) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(in_l + row * HS + col)), "l"(pl + row * H + col) : "memory");
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(in_r + row * HS + col)), "l"(pr + row * H + col) : "memory");
             }
@@ -119,13 +124,23 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
 
     // what the next tile needs from this one, per output of this thread's last-pass butterflies: lane f < 3 keeps the
     // partial sum of the older frames of hop F0 + 16 + f (see the overlap-add below)
-    float2 carry_y[ITB][SY], carry_c[SC];
+    constexpr bool CSM = fb_carry_in_smem<N>();
+    float2* carry_sm = cbuf + M * FB_QS + (jb * 3 + (q < 3 ? q : 0)) * 12;     // (CSM) this thread's 12 carries, lanes 0..2 only
+    float2 carry_y[CSM ? 1 : ITB][CSM ? 1 : SY], carry_c[CSM ? 1 : SC];
+    if constexpr (CSM) {
+        static_assert(ITB * SY + SC == 12, "carry layout");
+        if (q < 3) {
 #pragma unroll
-    for (int it = 0; it < ITB; it++)
+            for (int r = 0; r < 12; r++) carry_sm[r] = make_float2(0.f, 0.f);
+        }
+    } else {
 #pragma unroll
-        for (int r = 0; r < SY; r++) carry_y[it][r] = make_float2(0.f, 0.f);
+        for (int it = 0; it < ITB; it++)
 #pragma unroll
-    for (int r = 0; r < SC; r++) carry_c[r] = make_float2(0.f, 0.f);
+            for (int r = 0; r < SY; r++) carry_y[it][r] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < SC; r++) carry_c[r] = make_float2(0.f, 0.f);
+    }
 
     // hop = ((y[f-3] + y[f-2]) + y[f-1]) + y[f]: x0..x3 are this lane's contributions to the hops of frames f .. f+3
     auto overlap_add = [&](float2 x0, float2 x1, float2 x2, float2 x3, float2& carry) -> float2 {
@@ -219,12 +234,8 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
                 float2* __restrict__ p2m = buf + (M + k) * FB_QS + q;
                 const float g1 = __ldg(gain + k), g2 = __ldg(gain + k2);
                 const float2 wp = __ldg(b.tw_pack + k);
-                if (g1 == 0.f && g2 == 0.f) {                     // (merged tables: non-zero gains come first)
-                    const float2 zero = make_float2(0.f, 0.f);
-                    *p1 = zero; *p1m = zero; *p2 = zero; *p2m = zero;
-                    if (!fold) { cbuf[k * FB_QS + q] = zero; cbuf[(k2 & (M - 1)) * FB_QS + q] = zero; }
-                    return;
-                }
+                // (no shortcut for zero gains: this kernel serves dense bands; a zero gain gives exact zeros anyway, and
+                // straight-line items let the gain / twiddle loads of several items overlap)
                 const float2 a1 = *p1, b1 = *p1m, a2 = *p2, b2 = *p2m;
                 float2 c1, y1, y1m, c2, y2, y2m;
                 if constexpr (MODE == FB_MERGED) {
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
                     if (k > 0) cbuf[k2 * FB_QS + q] = zmk;
                 }
             };
-#pragma unroll 2
+#pragma unroll 4
             for (int i = 0; i < (M / 2) / JS; i++) mask_item(jb + i * JS);
             if (jb == 0) mask_item(M / 2);                        // bins M/2 and N - M/2: one pair, taken twice by the item code
         }
@@ -296,7 +307,14 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
                 for (int r = 0; r < RB; r++) v[it][r] = cscale(v[it][r], __ldg(syn + j + r * RA));
 #pragma unroll
                 for (int rr = 0; rr < SY; rr++) {
-                    const float2 s = overlap_add(v[it][rr], v[it][SY + rr], v[it][2 * SY + rr], v[it][3 * SY + rr], carry_y[it][rr]);
+                    float2 s;
+                    if constexpr (CSM) {
+                        float2 cy = q < 3 ? carry_sm[it * SY + rr] : make_float2(0.f, 0.f);
+                        s = overlap_add(v[it][rr], v[it][SY + rr], v[it][2 * SY + rr], v[it][3 * SY + rr], cy);
+                        if (q < 3) carry_sm[it * SY + rr] = cy;
+                    } else {
+                        s = overlap_add(v[it][rr], v[it][SY + rr], v[it][2 * SY + rr], v[it][3 * SY + rr], carry_y[it][rr]);
+                    }
                     const int m = j + rr * RA;
                     stage[(16 + q) * HS + m] = s.x;
                     stage[(32 + q) * HS + m] = s.y;
@@ -345,7 +363,14 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
                 }
 #pragma unroll
                 for (int rr = 0; rr < SC; rr++) {
-                    const float2 s = overlap_add(v[rr], v[SC + rr], v[2 * SC + rr], v[3 * SC + rr], carry_c[rr]);
+                    float2 s;
+                    if constexpr (CSM) {
+                        float2 cy = q < 3 ? carry_sm[ITB * SY + rr] : make_float2(0.f, 0.f);
+                        s = overlap_add(v[rr], v[SC + rr], v[2 * SC + rr], v[3 * SC + rr], cy);
+                        if (q < 3) carry_sm[ITB * SY + rr] = cy;
+                    } else {
+                        s = overlap_add(v[rr], v[SC + rr], v[2 * SC + rr], v[3 * SC + rr], carry_c[rr]);
+                    }
                     *reinterpret_cast<float2*>(stage + q * HS + 2 * (j + rr * HA)) = s;
                 }
             }
@@ -372,11 +397,11 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
 #pragma unroll
                             for (int i = 0; i < (16 * H / 2) / T; i++) pv[i] = __ldcs(reinterpret_cast<const float2*>(po) + tid + i * T);
                         }
+                        // T = 2H threads, H/2 float2 per hop row: a thread keeps its column, four hops further each time
+                        const float* __restrict__ sg0 = sg + (tid / (H / 2)) * HS + 2 * (tid & (H / 2 - 1));
 #pragma unroll
                         for (int i = 0; i < (16 * H / 2) / T; i++) {
-                            const int e = 2 * (tid + i * T);
-                            const int f = e / H, m = e - f * H;
-                            float2 s = *reinterpret_cast<const float2*>(sg + f * HS + m);
+                            float2 s = *reinterpret_cast<const float2*>(sg0 + 4 * i * HS);
                             if (ACCUM) s = make_float2(pv[i].x + s.x, pv[i].y + s.y);
                             __stcs(reinterpret_cast<float2*>(po) + tid + i * T, s);
                         }
