@@ -243,7 +243,7 @@ int run_dec_band(const UpmixPlan* p, const BandDev& b, const SegArgs& a, int n_t
 int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_begin, int64_t in_end,
                 int64_t n_total, int64_t seg_begin, int64_t seg_end, int n_tracks, int64_t in_stride, float* out_c,
                 float* out_l, float* out_r, int64_t out_stride, void* workspace, int64_t workspace_bytes,
-                float* const* band_state, cudaStream_t st, bool force_direct = false) {
+                float* const* band_state, cudaStream_t st, bool force_direct = false, float* const* band_state_tmp = nullptr) {
     const int64_t seg_len = seg_end - seg_begin;
     const int64_t prod_end = std::min(seg_end, n_total);      // nothing is produced past the end of the track
     const bool direct = seg_begin >= 0 && prod_end == seg_end &&
@@ -310,6 +310,7 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
         a.seg_begin = std::max<int64_t>(seg_begin, 0);
         a.seg_end = prod_end;
         a.state = band_state ? band_state[bi] : nullptr;
+        a.state_out = a.state;
         a.fold = p->fold_in_freq ? 1 : 0;
         if (!direct && (seg_begin < 0 || prod_end < seg_end)) {
             // part of the requested range lies outside the track: those samples are zero
@@ -337,8 +338,23 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
             CU_CHECK(launch_band_fb(b, a, n_runs, n_tracks, st));
         } else if (b.n_fft <= FUSED_MAX_N) {
             if (a.state) {
-                a.hops_per_run = (int)total_hops;              // the ring is carried: one CTA per track
-                CU_CHECK(launch_band_fused(b, a, 1, n_tracks, st));
+                // the ring is carried between calls.  A block that holds many hops of a small band (32 hops of a 256-point
+                // band in a 2048-sample Bela block) would be ONE CTA working through them one after the other -- the longest
+                // chain of the block (60 us of 99).  Such a band runs as several CTAs: run 0 loads the ring, the others
+                // replay their K-1 warm-up frames from the block itself (they start K-1 hops into it at the earliest), the
+                // last one saves the ring to a temporary that is copied over the state afterwards.  Same additions in the
+                // same order: bit-identical to the single run.
+                const int K = b.n_fft / b.hop;
+                int n_runs = 1;
+                a.hops_per_run = (int)total_hops;
+                if (band_state_tmp && band_state_tmp[bi] && K >= 2 && total_hops >= 2 * K && n_tracks <= 16) {
+                    a.hops_per_run = K - 1;
+                    n_runs = (int)((total_hops + a.hops_per_run - 1) / a.hops_per_run);
+                    a.state_out = band_state_tmp[bi];
+                }
+                CU_CHECK(launch_band_fused(b, a, n_runs, n_tracks, st));
+                if (a.state_out != a.state)
+                    CU_CHECK(cudaMemcpyAsync(a.state, a.state_out, (size_t)3 * b.n_fft * n_tracks * sizeof(float), cudaMemcpyDeviceToDevice, st));
             } else {
                 a.hops_per_run = pick_hops_per_run(p, b.n_fft, total_hops, n_tracks);
                 const int n_runs = (int)((total_hops + a.hops_per_run - 1) / a.hops_per_run);
@@ -681,6 +697,10 @@ int upmix_plan_destroy(UpmixPlan* plan) {
     }
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     for (UpmixPlan::GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
+    for (UpmixPlan::GraphEntry& g : plan->stream_graphs) {
+        cudaGraphExecDestroy(g.exec);
+        cudaGraphDestroy(g.graph);
+    }
     if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
     upmix_host_ctx_destroy(plan->host);
     cudaFree(plan->tables);
@@ -812,10 +832,87 @@ int upmix_stream_reset(const UpmixPlan* plan, void* state, int n_tracks, void* s
     return UPMIX_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// bytes of the temporary rings of split bands (see run_segment), one per band
+int64_t stream_tmp_ring_bytes(const UpmixPlan* plan, int n_tracks) {
+    int64_t floats = 0;
+    for (const BandDev& b : plan->bands) floats += round_up(3LL * b.n_fft * n_tracks, 64);
+    return round_up(floats * (int64_t)sizeof(float), 256);
+}
+
+struct StreamIo {
+    const float* in_l;
+    const float* in_r;
+    float* out_c;
+    float* out_l;
+    float* out_r;
+};
+
+// One block: stage = history ++ new block, every band over the block's output range (rings carried), band sum.
+// Under stream capture `stage_node` / `sum_node` receive the graph nodes of the two kernels that touch the caller's
+// input and output buffers (the only per-call pointers).
+int stream_block_body(const UpmixPlan* plan, void* state, int64_t pos, const StreamIo& io, int n_new, int n_tracks, int64_t in_stride,
+                      int64_t out_stride, void* workspace, int64_t workspace_bytes, cudaStream_t st, cudaGraphNode_t* stage_node,
+                      cudaGraphNode_t* sum_node) {
+    const int64_t D = plan->delay;
+    const int64_t span = D + n_new;
+    float* hist = reinterpret_cast<float*>(state);
+    float* stage = reinterpret_cast<float*>(workspace);       // [2][track][span]
+    const int64_t stage_bytes = round_up(2LL * n_tracks * span * (int64_t)sizeof(float), 256);
+    const int64_t tmp_bytes = stream_tmp_ring_bytes(plan, n_tracks);
+    auto last_node = [&](cudaGraphNode_t* out) {
+        if (!out) return;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t nd = 0;
+        *out = nullptr;
+        if (cudaStreamGetCaptureInfo(st, &cs, nullptr, nullptr, &deps, &nd) == cudaSuccess && cs == cudaStreamCaptureStatusActive && nd == 1)
+            *out = deps[0];
+    };
+    if (n_new <= 65536 && D <= 65536) {
+        CU_CHECK(launch_stream_stage(hist, stage, io.in_l, io.in_r, in_stride, (int)D, n_new, n_tracks, st));
+        last_node(stage_node);
+    } else {
+        // stage = history ++ new block (per channel, per track); history <- last D samples of stage
+        for (int ch = 0; ch < 2; ch++) {
+            const float* src = ch ? io.in_r : io.in_l;
+            float* dst = stage + (int64_t)ch * n_tracks * span;
+            CU_CHECK(cudaMemcpy2DAsync(dst, span * sizeof(float), hist + (int64_t)ch * n_tracks * D, D * sizeof(float),
+                                       D * sizeof(float), n_tracks, cudaMemcpyDeviceToDevice, st));
+            CU_CHECK(cudaMemcpy2DAsync(dst + D, span * sizeof(float), src, in_stride * sizeof(float), (size_t)n_new * sizeof(float),
+                                       n_tracks, cudaMemcpyDeviceToDevice, st));
+            CU_CHECK(cudaMemcpy2DAsync(hist + (int64_t)ch * n_tracks * D, D * sizeof(float), dst + n_new, span * sizeof(float),
+                                       D * sizeof(float), n_tracks, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    std::vector<float*> rings, tmps;
+    float* rp = hist + round_up(2 * D * n_tracks, 64);
+    float* tp = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + stage_bytes);
+    for (const BandDev& b : plan->bands) {
+        rings.push_back(rp);
+        tmps.push_back(tp);
+        rp += round_up(3LL * b.n_fft * n_tracks, 64);
+        tp += round_up(3LL * b.n_fft * n_tracks, 64);
+    }
+    const int64_t seg_begin = pos - D, seg_end = pos + n_new - D;
+    const int rc = run_segment(plan, stage, stage + (int64_t)n_tracks * span, seg_begin, pos + n_new, INT64_MAX / 4, seg_begin, seg_end,
+                               n_tracks, span, io.out_c, io.out_l, io.out_r, out_stride, reinterpret_cast<char*>(workspace) + stage_bytes + tmp_bytes,
+                               workspace_bytes - stage_bytes - tmp_bytes, rings.data(), st, false, tmps.data());
+    if (rc == UPMIX_OK) last_node(sum_node);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
 int64_t upmix_stream_workspace_bytes(const UpmixPlan* plan, int n_new, int n_tracks) {
     if (!plan || n_new < 1 || n_tracks < 1) return fail(UPMIX_E_INVALID, "bad arguments");
     const int64_t stage = round_up(2LL * n_tracks * (plan->delay + n_new) * (int64_t)sizeof(float), 256);
-    return stage + make_layout(plan, n_new, n_tracks, true).total;
+    return stage + stream_tmp_ring_bytes(plan, n_tracks) + make_layout(plan, n_new, n_tracks, true).total;
 }
 
 int upmix_stream_block(const UpmixPlan* plan, void* state, int64_t samples_done, const float* in_l, const float* in_r,
@@ -825,41 +922,104 @@ int upmix_stream_block(const UpmixPlan* plan, void* state, int64_t samples_done,
     if (rc) return rc;
     if (!state) return fail(UPMIX_E_INVALID, "state is NULL");
     if (n_new < 1 || samples_done < 0) return fail(UPMIX_E_INVALID, "bad n_new / samples_done");
+    int64_t n_max = 0;
     for (const BandDev& b : plan->bands) {
         if (b.n_fft > FUSED_MAX_N) return fail(UPMIX_E_UNSUPPORTED, "block streaming needs n_fft <= %d", FUSED_MAX_N);
         if (n_new % b.hop != 0 || samples_done % b.hop != 0)
             return fail(UPMIX_E_INVALID, "block of %d samples is not a multiple of hop %d", n_new, b.hop);
+        n_max = std::max<int64_t>(n_max, b.n_fft);
     }
     const int64_t need = upmix_stream_workspace_bytes(plan, n_new, n_tracks);
     if (workspace_bytes < need) return fail(UPMIX_E_WORKSPACE, "workspace too small: %lld given, %lld needed", (long long)workspace_bytes, (long long)need);
     DeviceGuard guard(plan->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int64_t D = plan->delay;
-    const int64_t span = D + n_new;
-    float* hist = reinterpret_cast<float*>(state);
-    float* stage = reinterpret_cast<float*>(workspace);       // [2][track][span]
-    const int64_t stage_bytes = round_up(2LL * n_tracks * span * (int64_t)sizeof(float), 256);
-    // stage = history ++ new block (per channel, per track); history <- last D samples of stage
-    for (int ch = 0; ch < 2; ch++) {
-        const float* src = ch ? in_r : in_l;
-        float* dst = stage + (int64_t)ch * n_tracks * span;
-        CU_CHECK(cudaMemcpy2DAsync(dst, span * sizeof(float), hist + (int64_t)ch * n_tracks * D, D * sizeof(float),
-                                   D * sizeof(float), n_tracks, cudaMemcpyDeviceToDevice, st));
-        CU_CHECK(cudaMemcpy2DAsync(dst + D, span * sizeof(float), src, in_stride * sizeof(float), (size_t)n_new * sizeof(float),
-                                   n_tracks, cudaMemcpyDeviceToDevice, st));
-        CU_CHECK(cudaMemcpy2DAsync(hist + (int64_t)ch * n_tracks * D, D * sizeof(float), dst + n_new, span * sizeof(float),
-                                   D * sizeof(float), n_tracks, cudaMemcpyDeviceToDevice, st));
+    const StreamIo io = {in_l, in_r, out_c, out_l, out_r};
+
+    // Steady state: a block's launches depend on its position only through (position mod n_fft) of each band -- ring
+    // slots and frame phases -- once every frame it touches exists (position >= 2 n_max).  So the position is folded into
+    // [2 n_max, 3 n_max), which makes the launches of blocks one n_max apart IDENTICAL, and the block is replayed as a
+    // CUDA graph: one launch instead of ~20 (the CPU-side launch cost was most of a block's wall time).  The caller's
+    // input / output pointers change from block to block; only the staging kernel and the band sum see them, and their
+    // graph nodes get the new pointers (cudaGraphExecKernelNodeSetParams) before the replay.
+    UpmixPlan* mp = const_cast<UpmixPlan*>(plan);
+    const int64_t pos = samples_done >= 2 * n_max ? 2 * n_max + samples_done % n_max : samples_done;
+    if (mp->use_graphs && mp->cap_stream && samples_done >= 2 * n_max && n_new <= 65536 && plan->delay <= 65536) {
+        const uint64_t align16 = ((reinterpret_cast<uintptr_t>(out_l) | reinterpret_cast<uintptr_t>(out_r) | reinterpret_cast<uintptr_t>(out_c)) & 15) == 0;
+        uint64_t key[16] = {(uint64_t)(uintptr_t)state, (uint64_t)pos, (uint64_t)n_new, (uint64_t)n_tracks, (uint64_t)in_stride, (uint64_t)out_stride,
+                            (uint64_t)(uintptr_t)workspace, (uint64_t)workspace_bytes, align16, out_c ? 1u : 0u, 0, 0, 0, 0, 0, 0x5354524dull /* "STRM" */};
+        for (UpmixPlan::GraphEntry& g : mp->stream_graphs)
+            if (memcmp(g.key, key, sizeof(key)) == 0) {
+                g.last_use = ++mp->graph_clock;
+                if (g.io[0] != in_l || g.io[1] != in_r) {
+                    cudaKernelNodeParams kp;
+                    CU_CHECK(cudaGraphKernelNodeGetParams(g.stage_node, &kp));
+                    void* args[8];
+                    for (int i = 0; i < 8; i++) args[i] = kp.kernelParams[i];
+                    args[2] = (void*)&in_l;
+                    args[3] = (void*)&in_r;
+                    kp.kernelParams = args;
+                    CU_CHECK(cudaGraphExecKernelNodeSetParams(g.exec, g.stage_node, &kp));
+                    g.io[0] = in_l;
+                    g.io[1] = in_r;
+                }
+                if (g.io[2] != out_c || g.io[3] != out_l || g.io[4] != out_r) {
+                    cudaKernelNodeParams kp;
+                    CU_CHECK(cudaGraphKernelNodeGetParams(g.sum_node, &kp));
+                    void* args[10];
+                    for (int i = 0; i < 10; i++) args[i] = kp.kernelParams[i];
+                    args[5] = (void*)&out_c;
+                    args[6] = (void*)&out_l;
+                    args[7] = (void*)&out_r;
+                    kp.kernelParams = args;
+                    CU_CHECK(cudaGraphExecKernelNodeSetParams(g.exec, g.sum_node, &kp));
+                    g.io[2] = out_c;
+                    g.io[3] = out_l;
+                    g.io[4] = out_r;
+                }
+                CU_CHECK(cudaGraphLaunch(g.exec, st));
+                launch_count_add(g.n_kernels);
+                return UPMIX_OK;
+            }
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        const bool caller_capturing = st && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+        if (!caller_capturing && cudaStreamBeginCapture(mp->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const unsigned long long before = launch_count(false);
+            cudaGraphNode_t stage_node = nullptr, sum_node = nullptr;
+            const int rc2 = stream_block_body(plan, state, pos, io, n_new, n_tracks, in_stride, out_stride, workspace, workspace_bytes,
+                                              mp->cap_stream, &stage_node, &sum_node);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ee = cudaStreamEndCapture(mp->cap_stream, &graph);
+            cudaGraphExec_t exec = nullptr;
+            if (rc2 == UPMIX_OK && ee == cudaSuccess && graph && stage_node && sum_node && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                UpmixPlan::GraphEntry g;
+                memcpy(g.key, key, sizeof(key));
+                g.exec = exec;
+                g.graph = graph;                               // kept: the node handles and their parameter storage live in it
+                g.stage_node = stage_node;
+                g.sum_node = sum_node;
+                g.io[0] = in_l; g.io[1] = in_r; g.io[2] = out_c; g.io[3] = out_l; g.io[4] = out_r;
+                g.n_kernels = (int)(launch_count(false) - before);
+                g.last_use = ++mp->graph_clock;
+                if (mp->stream_graphs.size() >= 16) {          // evict the least recently used
+                    size_t lru = 0;
+                    for (size_t i = 1; i < mp->stream_graphs.size(); i++)
+                        if (mp->stream_graphs[i].last_use < mp->stream_graphs[lru].last_use) lru = i;
+                    cudaGraphExecDestroy(mp->stream_graphs[lru].exec);
+                    cudaGraphDestroy(mp->stream_graphs[lru].graph);
+                    mp->stream_graphs[lru] = g;
+                } else {
+                    mp->stream_graphs.push_back(g);
+                }
+                CU_CHECK(cudaGraphLaunch(exec, st));
+                return UPMIX_OK;
+            }
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();                                 // capture failed: run the block the plain way
+            if (rc2 != UPMIX_OK) return rc2;
+        }
     }
-    std::vector<float*> rings;
-    float* rp = hist + round_up(2 * D * n_tracks, 64);
-    for (const BandDev& b : plan->bands) {
-        rings.push_back(rp);
-        rp += round_up(3LL * b.n_fft * n_tracks, 64);
-    }
-    const int64_t seg_begin = samples_done - D, seg_end = samples_done + n_new - D;
-    return run_segment(plan, stage, stage + (int64_t)n_tracks * span, seg_begin, samples_done + n_new, INT64_MAX / 4, seg_begin,
-                       seg_end, n_tracks, span, out_c, out_l, out_r, out_stride, reinterpret_cast<char*>(workspace) + stage_bytes,
-                       workspace_bytes - stage_bytes, rings.data(), st);
+    return stream_block_body(plan, state, pos, io, n_new, n_tracks, in_stride, out_stride, workspace, workspace_bytes, st, nullptr, nullptr);
 }
 
 int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, const float* blk_l, const float* blk_r,

@@ -130,8 +130,9 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
                       a.out_r + (long long)track * a.out_stride};
     float* st_ring = a.state ? a.state + (long long)track * 3 * N : nullptr;
 
+    const bool st_load = st_ring && blockIdx.x == 0;
     long long f_begin;
-    if (st_ring) {
+    if (st_load) {
         f_begin = h0;
         const int nb0 = (int)(h0 % K) * H;          // slot 0 of the saved ring = first sample of frame h0
         for (int i = tid; i < 3 * N; i += T) {
@@ -591,13 +592,14 @@ __global__ void __launch_bounds__(FusedCfg<N>::T) __maxnreg__(FusedCfg<N>::MAXRE
         }
         __syncthreads();
     }
-    if (st_ring) {
+    if (st_ring && h1 == a.hop_end) {
         // re-base the ring so that slot 0 is the first unfinished sample (frame h1 starts there)
+        float* st_save = a.state_out + (long long)track * 3 * N;
         const int nb = (int)(h1 % K) * H;
         for (int i = tid; i < 3 * N; i += T) {
             const int ch = i / N, n = i - ch * N;
             // FE leaves the emitted hop in the ring (the next frame overwrites it): it reads as zero in the state
-            st_ring[i] = FE && n >= N - H ? 0.f : ring[ch * N + ((nb + n) & (N - 1))];
+            st_save[i] = FE && n >= N - H ? 0.f : ring[ch * N + ((nb + n) & (N - 1))];
         }
     }
 }

@@ -538,6 +538,23 @@ __global__ void __launch_bounds__(256) band_sum_kernel(const float* __restrict__
     }
 }
 
+// Block streaming: stage = history ++ new block, history <- last D samples of stage, per channel and track (one CTA
+// each: the barrier orders the in-place shift of the history).  Replaces six cudaMemcpy2DAsync per block.
+__global__ void __launch_bounds__(1024) stream_stage_kernel(float* __restrict__ hist, float* __restrict__ stage,
+                                                            const float* __restrict__ in_l, const float* __restrict__ in_r,
+                                                            long long in_stride, int D, int n_new, int n_tracks) {
+    const int ch = blockIdx.x, track = blockIdx.y;
+    const int span = D + n_new;
+    float* __restrict__ h = hist + ((long long)ch * n_tracks + track) * D;
+    float* __restrict__ s = stage + ((long long)ch * n_tracks + track) * span;
+    const float* __restrict__ src = (ch ? in_r : in_l) + (long long)track * in_stride;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < span; i += blockDim.x) s[i] = i < D ? h[i] : __ldg(src + (i - D));
+    __syncthreads();
+#pragma unroll 4
+    for (int j = threadIdx.x; j < D; j += blockDim.x) h[j] = s[n_new + j];
+}
+
 // ---------------------------------------------------------------------------------------------
 // main.py's tail on the device (main.py:85-97, 110-157): peak of the three outputs, then one scale
 // factor and the export mix written as interleaved stereo.
@@ -899,6 +916,13 @@ cudaError_t launch_col_inv_ola(const BandDev& b, const SegArgs& a, const WaveArg
         else col_inv_ola_kernel<false, false><<<grid, 128, 0, st>>>(b, a, w);
     }
     g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stream_stage(float* hist, float* stage, const float* in_l, const float* in_r, long long in_stride, int D,
+                                int n_new, int n_tracks, cudaStream_t st) {
+    g_launches++;
+    stream_stage_kernel<<<dim3(2, n_tracks), 1024, 0, st>>>(hist, stage, in_l, in_r, in_stride, D, n_new, n_tracks);
     return cudaGetLastError();
 }
 

@@ -72,6 +72,11 @@ struct SegArgs {
     int fold;                       // fused kernel: fold the centre in the frequency domain -- emit
                                     // Ls + 0.5 C and Rs + 0.5 C in the Ls / Rs slots, no C transform
     float* state;                   // optional streaming state [track][3][n_fft]: ring carried between calls
+    float* state_out;               // where the ring is saved (state == nullptr: unused).  One run per track: the CTA loads
+                                    // `state` and saves to `state_out` (may be the same memory).  Several runs per track
+                                    // (hops_per_run >= 3): run 0 loads `state`, the others replay their three warm-up frames
+                                    // from the input like an offline call, and the run that ends at hop_end saves -- to a
+                                    // DIFFERENT buffer, which the host copies over `state` afterwards (run 0 may load late)
     int accum;                      // 0: finished samples are stored;  1: added to what out_* already holds
                                     // (float32, band order = launch order: center_extraction.py:503-511)
     int mix;                        // 0: out_c/out_l/out_r receive C, Ls, Rs;  1: fold-down epilogue --

@@ -28,6 +28,10 @@ cudaError_t launch_band_sum(const float* ws, int n_bands, int n_tracks, long lon
                             float* out_c, float* out_l, float* out_r, long long out_stride, int mode,
                             cudaStream_t st);
 
+// block streaming: stage = history ++ new block; history <- the last D samples of stage ([2][track][D] / [2][track][D + n_new])
+cudaError_t launch_stream_stage(float* hist, float* stage, const float* in_l, const float* in_r, long long in_stride, int D,
+                                int n_new, int n_tracks, cudaStream_t st);
+
 cudaError_t launch_pcm16_to_planar(const short* in, long long n, float* l, float* r, float* partial, int n_blocks, float* peak,
                                    cudaStream_t st);
 cudaError_t launch_stereo_to_pcm16(const float* in, long long n, short* out, cudaStream_t st);

@@ -39,8 +39,14 @@ struct UpmixPlan {
         cudaGraphExec_t exec;
         int n_kernels;
         uint64_t last_use;
+        // block streaming only: the graph itself (owner of the node handles), the two nodes that see the caller's
+        // buffers and the pointers they currently hold (in_l, in_r, out_c, out_l, out_r)
+        cudaGraph_t graph = nullptr;
+        cudaGraphNode_t stage_node = nullptr, sum_node = nullptr;
+        const void* io[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     };
     std::vector<GraphEntry> graphs;
+    std::vector<GraphEntry> stream_graphs;   // steady-state blocks of upmix_stream_block, keyed on the folded position
     cudaStream_t cap_stream = nullptr;
     uint64_t graph_clock = 0;
     bool use_graphs = true;
