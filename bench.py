@@ -14,6 +14,7 @@ Workloads (config.workload):
   cfg5 (configs[4]): 512 synthetic 5-minute tracks (seeds 1000..1511), main.py's default six bands, track i on rank
        i mod N (upmix_b200.sharding.tracks_for_rank), processed in waves of tracks per GPU ("scaling": "strong").
   cfg1 (configs[0] shape): 10 s, default six bands.
+  cfg3-stream: the Bela program's bands, one 2048-sample hardware block per call (latency of upmix_stream_block).
 
 `value`: inputs resident in HBM, CUDA events on the launching stream, max over ranks.  `e2e`: the same metric through
 the public call `extract_center_left_right_multi_band_in_memory` with pinned HOST tensors (H2D and D2H inside the
@@ -54,6 +55,9 @@ WORKLOADS = {
                       "65536/65536/16384/4096/1024/256), track i on rank i mod N, waves of tracks per GPU, Ls/C/Rs out"),
     "cfg1": dict(edges=[0.0, 30.0, 120.0, 480.0, 1920.0, 7680.0], seconds=10, tracks=1, per_rank=True,
                  text="cfg1 shape: 10 s 48 kHz stereo, main.py's default 6 bands, Ls/C/Rs out"),
+    "cfg3-stream": dict(edges=[0.0, 500.0, 2000.0, 8000.0], seconds=60, tracks=1, per_rank=True,
+                        text="cfg3 block streaming: the Bela program's 4 bands (bela/upmix.cpp:498-514; STFT 8192/4096/1024/256 at "
+                             "hwBlock 2048), L+0.5C / R+0.5C out, one hardware block per call with carried state (upmix_stream_block)"),
 }
 
 
@@ -190,6 +194,59 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_stream(args, local_rank):
+    """--workload cfg3-stream: latency of one hardware block of the Bela-equivalent streaming mode.  One step = 100 blocks
+    queued back to back on one stream (device timeline, CUDA events); `wall_us_per_block` = submit one block and wait."""
+    import contextlib
+    import io
+    import torch
+    from upmix_b200 import _native, bela
+    torch.cuda.set_device(local_rank)
+    hw = args.hw_block
+    up = bela.MultiBandUpmix()
+    with contextlib.redirect_stdout(io.StringIO()):
+        up.setup(hw, float(SR), 4, WORKLOADS["cfg3-stream"]["edges"] + [24000.0])
+    per_step = 100
+    total = (args.warmup + args.steps) * per_step + 150
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = 0.1 * torch.randn(2, hw * total, device="cuda", generator=g)
+    i = 0
+    for _ in range(args.warmup * per_step):
+        up.process(x[0, i * hw:(i + 1) * hw], x[1, i * hw:(i + 1) * hw])
+        i += 1
+    torch.cuda.synchronize()
+    _native.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps * per_step):
+        up.process(x[0, i * hw:(i + 1) * hw], x[1, i * hw:(i + 1) * hw])
+        i += 1
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _native.launch_count()
+    ms_per_step = e0.elapsed_time(e1) / args.steps
+    us_block = ms_per_step * 1e3 / per_step
+    wall = []
+    for _ in range(100):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        up.process(x[0, i * hw:(i + 1) * hw], x[1, i * hw:(i + 1) * hw])
+        torch.cuda.synchronize()
+        wall.append(time.perf_counter() - t0)
+        i += 1
+    wall.sort()
+    sizes = [b.block_size for b in up.bands]
+    line = {"metric": "realtime factor (audio-s/s, 48 kHz stereo)", "value": hw / SR / (us_block * 1e-6), "unit": "audio-s/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS["cfg3-stream"]["text"], "hw_block": hw, "blocks_per_step": per_step, "stft_sizes": sizes,
+                       "note": "latency workload (not the headline): inputs and state stay in L2"},
+            "us_per_block": us_block, "wall_us_per_block": {"median": wall[len(wall) // 2] * 1e6, "min": wall[0] * 1e6,
+                                                            "what": "python call + one graph launch + synchronize"},
+            "block_ms_of_audio": hw / SR * 1e3, "gpu_launches": int(launches)}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,6 +258,7 @@ def main():
     ap.add_argument("--seconds", type=int, default=0, help="override the track length (marks the line as REDUCED)")
     ap.add_argument("--tracks", type=int, default=0, help="cfg5: override the number of tracks (marks the line as REDUCED)")
     ap.add_argument("--wave-tracks", type=int, default=32, help="cfg5: tracks per wave on one GPU")
+    ap.add_argument("--hw-block", type=int, default=2048, help="cfg3-stream: samples per hardware block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -209,6 +267,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "cfg3-stream" and args.impl == "ours":
+        if rank == 0:
+            run_stream(args, local_rank)
+        return
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -483,6 +483,48 @@ def test_fold_down_with_large_band_and_stream_multitrack(ce):
         assert float((dflt[ch] - off[ch]).abs().max()) < 1e-6
 
 
+def test_stream_graph_replay_and_split_runs_are_bit_identical(ce):
+    """Steady-state blocks are replayed as CUDA graphs (position folded modulo the largest STFT size, caller buffers
+    patched into two graph nodes) and small bands run as several CTAs per block: same stream, bit for bit, as a plan
+    that launches every block the plain way -- with input / output buffers that move from block to block, two block
+    sizes, and a block-size change in mid-stream."""
+    import torch
+    from upmix_b200 import _native
+    sr = 48000
+    bands = quiet(ce.chain_bands, [0, 700, 3000, 9000], 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=4096)
+    n = 4096 * 14
+    L, R = uo.synth_stereo(n, 31, stress=True)
+    A, B = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    tables = [b.plan_tables() for b in bands]
+    os.environ["UPMIX_GRAPHS"] = "0"
+    try:
+        plain = _native.Plan(tables, _native.OUT_LSCRS, flags=_native.PLAN_STREAM_KERNELS)
+    finally:
+        os.environ.pop("UPMIX_GRAPHS")
+    graphed = _native.Plan(tables, _native.OUT_LSCRS, flags=_native.PLAN_STREAM_KERNELS)
+    off = graphed.process(A, B)
+    for sizes in ([1024] * 56, [2048] * 28, [1024] * 20 + [4096] * 6 + [1024] * 12):
+        outs = []
+        for plan in (plain, graphed):
+            st = plan.stream_open(1)
+            pos, keep, blocks = 0, [], []
+            for k, m in enumerate(sizes):
+                # fresh (moving) buffers: slices at odd offsets of a scratch tensor, kept alive so that pointers differ
+                scratch = torch.empty(2, m + 8, device="cuda")
+                o = 4 * (k % 2)
+                scratch[0, o:o + m] = A[pos:pos + m]
+                scratch[1, o:o + m] = B[pos:pos + m]
+                keep.append(scratch)
+                blocks.append(st.block(scratch[0, o:o + m], scratch[1, o:o + m]))
+                pos += m
+            assert pos == n
+            outs.append([torch.cat([b[ch] for b in blocks]) for ch in range(3)])
+        d = graphed.stream_open(1).delay
+        for ch in range(3):
+            assert torch.equal(outs[0][ch], outs[1][ch]), (sizes[:3], ch)
+            assert torch.equal(outs[1][ch][d:], off[ch][:n - d])
+
+
 def test_pcm16_edge_kernels(ce):
     """WAV edge on the device: int16 stereo -> planar float32 + peak, float32 stereo -> int16."""
     import torch

@@ -172,3 +172,43 @@ def test_bela_rules_use_float32_like_the_cpp():
     # 48000*32/f_low exactly a power of two in float32 but not in float64 -> the size flips if float64 is used
     f_low = float(np.nextafter(np.float32(1536000.0 / 1024.0), np.float32(0)))       # just below 1500 Hz
     assert bela.compute_block_size_bela(f_low, 48000.0, 2048) in (1024, 2048)
+
+
+def test_host_conversion_loops_match_numpy():
+    """upmix_simd.cpp (AVX2 / non-temporal stores behind a CPU check): float64 / float32 interleaved -> planar float32,
+    strided gathers and the copy-out loop give exactly numpy's astype(float32), for ragged lengths and misaligned
+    destinations."""
+    import ctypes
+    from upmix_b200 import _native
+    lib = _native.load_library()
+    i64, vp = ctypes.c_int64, ctypes.c_void_p
+    for name, at in (("upmix_host_pair_f64", [vp, i64, vp, vp]), ("upmix_host_pair_f32", [vp, i64, vp, vp]),
+                     ("upmix_host_gather_f64", [vp, i64, i64, vp]), ("upmix_host_gather_f32", [vp, i64, i64, vp]),
+                     ("upmix_host_copy", [vp, vp, i64])):
+        getattr(lib, name).argtypes = at
+        getattr(lib, name).restype = None
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 8, 33, 1000, 4099):
+        for off_l, off_r in ((0, 0), (3, 3), (1, 6)):
+            w64 = rng.standard_normal((n, 2)) * 1e3
+            w32 = w64.astype(np.float32)
+            for src, fn in ((w64, lib.upmix_host_pair_f64), (w32, lib.upmix_host_pair_f32)):
+                bl, br = np.full(n + 16, 7.0, np.float32), np.full(n + 16, 7.0, np.float32)
+                dl, dr = bl[off_l:off_l + n], br[off_r:off_r + n]
+                fn(src.ctypes.data, n, dl.ctypes.data, dr.ctypes.data)
+                assert np.array_equal(dl, src[:, 0].astype(np.float32)) and np.array_equal(dr, src[:, 1].astype(np.float32))
+                assert (bl[:off_l] == 7).all() and (bl[off_l + n:] == 7).all() and (br[:off_r] == 7).all() and (br[off_r + n:] == 7).all()
+            for stride in (1, 3):
+                x64 = rng.standard_normal(n * stride + 1)
+                x32 = x64.astype(np.float32)
+                for src, fn in ((x64, lib.upmix_host_gather_f64), (x32, lib.upmix_host_gather_f32)):
+                    buf = np.full(n + 16, 7.0, np.float32)
+                    d = buf[off_l:off_l + n]
+                    fn(src.ctypes.data, stride, n, d.ctypes.data)
+                    assert np.array_equal(d, src[:n * stride:stride].astype(np.float32))
+                    assert (buf[:off_l] == 7).all() and (buf[off_l + n:] == 7).all()
+    big = rng.standard_normal(70001).astype(np.float32)
+    for off in (0, 1, 5):
+        buf = np.full(big.size + 16, 7.0, np.float32)
+        lib.upmix_host_copy(buf[off:].ctypes.data, big.ctypes.data, big.size)
+        assert np.array_equal(buf[off:off + big.size], big) and (buf[:off] == 7).all() and (buf[off + big.size:] == 7).all()

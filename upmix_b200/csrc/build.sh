@@ -10,8 +10,10 @@ for s in $SRCS; do
     $NVCC $FLAGS -c $s.cu -o $s.o &
     pids="$pids $!"
 done
+${CXX:-g++} -O3 -std=c++17 -fPIC -c upmix_simd.cpp -o upmix_simd.o &
+pids="$pids $!"
 for p in $pids; do wait $p; done
-OBJS=""
+OBJS="upmix_simd.o"
 for s in $SRCS; do OBJS="$OBJS $s.o"; done
 $NVCC $FLAGS -shared -o libupmix_b200.so $OBJS
 echo "built $(pwd)/libupmix_b200.so"

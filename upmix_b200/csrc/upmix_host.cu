@@ -104,24 +104,16 @@ bool wait_flag(const std::atomic<int>& flag, const std::atomic<int>& err) {
     return true;
 }
 
-template <class Tin>
-void gather_chunk(const Tin* src, int64_t stride, int64_t n, float* dst) {
-    if (stride == 1) {
-        for (int64_t i = 0; i < n; i++) dst[i] = (float)src[i];
-    } else {
-        for (int64_t i = 0; i < n; i++) dst[i] = (float)src[i * stride];
-    }
-}
-// L and R interleaved in one array (main.py:49-50: wave[:, 0], wave[:, 1]): one pass over the memory
-template <class Tin>
-void gather_chunk_pair(const Tin* src, int64_t n, float* dl, float* dr) {
-    for (int64_t i = 0; i < n; i++) {
-        dl[i] = (float)src[2 * i];
-        dr[i] = (float)src[2 * i + 1];
-    }
-}
-
 }  // namespace
+
+// conversion / copy loops (upmix_simd.cpp: AVX2 with non-temporal stores behind a run-time CPU check)
+extern "C" {
+void upmix_host_pair_f64(const double* src, int64_t n, float* dl, float* dr);
+void upmix_host_pair_f32(const float* src, int64_t n, float* dl, float* dr);
+void upmix_host_gather_f64(const double* src, int64_t stride, int64_t n, float* dst);
+void upmix_host_gather_f32(const float* src, int64_t stride, int64_t n, float* dst);
+void upmix_host_copy(float* dst, const float* src, int64_t n);
+}
 
 extern "C" {
 
@@ -292,16 +284,16 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
             float* sl = c.pin_in + (int64_t)slot * 2 * slot_len;
             float* sr = sl + slot_len;
             if (dtype == UPMIX_F64) {
-                if (paired) gather_chunk_pair((const double*)L + 2 * a, len, sl, sr);
+                if (paired) upmix_host_pair_f64((const double*)L + 2 * a, len, sl, sr);
                 else {
-                    gather_chunk((const double*)L + a * stride_l, stride_l, len, sl);
-                    gather_chunk((const double*)R + a * stride_r, stride_r, len, sr);
+                    upmix_host_gather_f64((const double*)L + a * stride_l, stride_l, len, sl);
+                    upmix_host_gather_f64((const double*)R + a * stride_r, stride_r, len, sr);
                 }
             } else {
-                if (paired) gather_chunk_pair((const float*)L + 2 * a, len, sl, sr);
+                if (paired) upmix_host_pair_f32((const float*)L + 2 * a, len, sl, sr);
                 else {
-                    gather_chunk((const float*)L + a * stride_l, stride_l, len, sl);
-                    gather_chunk((const float*)R + a * stride_r, stride_r, len, sr);
+                    upmix_host_gather_f32((const float*)L + a * stride_l, stride_l, len, sl);
+                    upmix_host_gather_f32((const float*)R + a * stride_r, stride_r, len, sr);
                 }
             }
             const auto t2 = clk::now();
@@ -323,7 +315,7 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
             const float* slot = c.pin_out + (int64_t)(p % c.ns_out) * 3 * slot_len;
             const auto t0 = clk::now();
             for (int ch = ch0; ch < 3; ch++)
-                memcpy(h_o[ch] + pieces[p].a, slot + (int64_t)ch * slot_len, (size_t)pieces[p].len * sizeof(float));
+                upmix_host_copy(h_o[ch] + pieces[p].a, slot + (int64_t)ch * slot_len, pieces[p].len);
             t_copyout[w & 63] += secs(t0, clk::now());
             out_done[p].store(1, std::memory_order_release);
         }
