@@ -45,6 +45,10 @@ namespace upmix {
 
 constexpr int DEC_QS = 17;        // row stride (float2) of a 16-column tile: odd, so that column-wise walks
                                   // (lanes = consecutive rows) are as conflict-free as row-wise ones
+#ifndef UPMIX_DEC_PREV_AHEAD
+#define UPMIX_DEC_PREV_AHEAD 1    // accumulating bands: the previous sums of a hop are requested one frame ahead (two buffers)
+#endif
+constexpr int DEC_PREV_BUFS = UPMIX_DEC_PREV_AHEAD ? 2 : 1;
 
 // second-pass twiddles of this thread's butterfly: w[r] = exp(-2 pi i r k / P), r = 1..15, as eight 16-byte loads
 __device__ __forceinline__ void load_tw16(const float2* __restrict__ tw_last, int k, float2 (&w)[16]) {
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
     constexpr int NST = CM == DEC_C16 ? 2 : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* buf = reinterpret_cast<float2*>(smem_raw);           // [P][DEC_QS]
-    float* prevbuf = reinterpret_cast<float*>(buf + P * DEC_QS);  // ACCUM: [2 regions][P/4 rows][16] previous sums of the hop
+    float* prevbuf = reinterpret_cast<float*>(buf + P * DEC_QS);  // ACCUM: [DEC_PREV_BUFS][2 regions][P/4 rows][16] previous sums of the hop
     constexpr int RSZ = (P / 4) * 16;
     const int tid = threadIdx.x, q = tid & 15, jb = tid >> 4;
     const int g = blockIdx.y, track = blockIdx.z;
@@ -247,6 +251,43 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
         for (int r = 0; r < 12; r++) acc[it][r] = make_float2(0.f, 0.f);
 
     const int n_iter = a.hops_per_run + 3;
+    // ACCUM (this band adds to what the outputs hold: the bands before it, in band order): the hop a frame finishes is
+    // copied asynchronously (cp.async, no registers) from the outputs into shared memory and read there by the last pass
+    // -- loaded at the store, the dependent HBM round trips cost 25 % of the kernel.  Two regions of P/4 rows x 16 floats:
+    // Ls / Rs rows of the tile (DEC_Y), the two 16-sequence halves (DEC_C32), the two runs (DEC_C16).  Hops cut by a
+    // segment edge, or not 16-byte aligned, take the plain loads below.  A frame lasts about as long as a trip to HBM,
+    // so the request goes out ONE FRAME AHEAD (two buffers, frame i uses buffer i & 1): issued at the top of frame i - 1,
+    // waited for before the last pass of frame i.
+    auto request_prev = [&](int i) -> bool {
+        const float* gsrc[2];
+        bool ok = i < n_iter;
+#pragma unroll
+        for (int rg = 0; rg < 2; rg++) {
+            const int s = NST == 2 ? rg : 0;
+            const long long f = h0s[s] - 3 + i;
+            const bool valid_s = h0s[s] < h1s[s] && f >= 0 && f < h1s[s];
+            const long long sb = f * H;
+            ok = ok && valid_s && f >= h0s[s] && sb >= a.seg_begin && sb + H <= a.seg_end;
+            const float* base = (CM == DEC_Y ? (rg ? a.out_r : a.out_l) : a.out_c) + (long long)track * a.out_stride + (sb - a.out_begin);
+            gsrc[rg] = base + (CM == DEC_Y ? 16 * g : CM == DEC_C32 ? 32 * g + 16 * rg : 0);
+            ok = ok && (reinterpret_cast<uintptr_t>(gsrc[rg]) & 15) == 0;
+        }
+        if (ok) {
+            float* pb = prevbuf + (DEC_PREV_BUFS == 2 ? (i & 1) * 2 * RSZ : 0);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c = tid + k * (P / 2);                 // 2 regions x P chunks of 16 bytes
+                const int rg = c / P, row = (c % P) >> 2, c4 = c & 3;
+                const float* src = gsrc[rg] + Q * row + 4 * c4;
+                const uint32_t dst = smem_u32(pb + rg * RSZ + row * 16 + 4 * c4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");     // (an empty group when nothing was requested)
+        return ok;
+    };
+    bool staged_next = false;
+    if constexpr (ACCUM && DEC_PREV_BUFS == 2) staged_next = request_prev(0);
 #pragma unroll 1
     for (int i = 0; i < n_iter; i++) {
         long long fs[NST];
@@ -257,39 +298,17 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
             valid[s] = h0s[s] < h1s[s] && fs[s] >= 0 && fs[s] < h1s[s];
             any = any || valid[s];
         }
-        if (!any) continue;                                      // CTA-uniform: nothing has been accumulated yet
-
-        // ACCUM (this band adds to what the outputs hold: the bands before it, in band order): the hop this frame
-        // finishes is copied asynchronously (cp.async, no registers) from the outputs into shared memory now and read
-        // there by the last pass -- loaded at the store, the dependent HBM round trips cost 25 % of the kernel.  Two
-        // regions of P/4 rows x 16 floats: Ls / Rs rows of the tile (DEC_Y), the two 16-sequence halves (DEC_C32), the two
-        // runs (DEC_C16).  Hops cut by a segment edge, or not 16-byte aligned, take the plain loads below.
         bool staged_prev = false;
         if constexpr (ACCUM) {
-            const float* gsrc[2];
-            bool ok = true;
-#pragma unroll
-            for (int rg = 0; rg < 2; rg++) {
-                const int s = NST == 2 ? rg : 0;
-                const long long sb = fs[s] * H;
-                ok = ok && valid[s] && fs[s] >= h0s[s] && sb >= a.seg_begin && sb + H <= a.seg_end;
-                const float* base = (CM == DEC_Y ? (rg ? a.out_r : a.out_l) : a.out_c) + (long long)track * a.out_stride + (sb - a.out_begin);
-                gsrc[rg] = base + (CM == DEC_Y ? 16 * g : CM == DEC_C32 ? 32 * g + 16 * rg : 0);
-                ok = ok && (reinterpret_cast<uintptr_t>(gsrc[rg]) & 15) == 0;
-            }
-            staged_prev = ok;
-            if (ok) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int c = tid + k * (P / 2);                 // 2 regions x P chunks of 16 bytes
-                    const int rg = c / P, row = (c % P) >> 2, c4 = c & 3;
-                    const float* src = gsrc[rg] + Q * row + 4 * c4;
-                    const uint32_t dst = smem_u32(prevbuf + rg * RSZ + row * 16 + 4 * c4);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
+            if constexpr (DEC_PREV_BUFS == 2) {
+                staged_prev = staged_next;
+                staged_next = request_prev(i + 1);
+            } else {
+                if (any) staged_prev = request_prev(i);
             }
         }
+        if (!any) continue;                                      // CTA-uniform: nothing has been accumulated yet
+        const float* __restrict__ prevcur = prevbuf + (DEC_PREV_BUFS == 2 ? (i & 1) * 2 * RSZ : 0);
 
         // ---- expansion: live bins -> U_q[s] for the tile's columns, written column-wise (lanes = slots) ----
         if constexpr (CM == DEC_Y) {
@@ -417,7 +436,9 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
             }
         }
         if constexpr (ACCUM) {
-            if (staged_prev) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            // this frame's previous sums have landed (the request for the next frame may still be in flight)
+            if constexpr (DEC_PREV_BUFS == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
 
@@ -464,7 +485,7 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_inv_kernel(const BandDev 
                     const float2 tot = __ffma2_rn(u[r], ww, acc[it][r]);
                     const int n1 = m1 + r * R0 * Q, n2 = m2 + r * R0 * Q;
                     if (ACCUM && staged_prev) {                       // row p = j + r*R0 of the staged hop
-                        const float* pb = prevbuf + (j + r * R0) * 16;
+                        const float* pb = prevcur + (j + r * R0) * 16;
                         prev[r] = CM == DEC_C16 ? make_float2(pb[sid * RSZ + (q & 7)], pb[sid * RSZ + 8 + (q & 7)])
                                                 : make_float2(pb[q], pb[RSZ + q]);
                     }

@@ -20,7 +20,7 @@ static cudaError_t dec_fwd_pq(const BandDev& b, const SegArgs& a, const DecWave&
 
 template <int P, int Q, bool CENTRE, bool ACCUM>
 static cudaError_t dec_inv_pqca(const BandDev& b, const SegArgs& a, const DecWave& w, int n_runs, int n_tracks, cudaStream_t st) {
-    const int smem = P * DEC_QS * (int)sizeof(float2) + (ACCUM ? 2 * (P / 4) * 16 * (int)sizeof(float) : 0);
+    const int smem = P * DEC_QS * (int)sizeof(float2) + (ACCUM ? DEC_PREV_BUFS * 2 * (P / 4) * 16 * (int)sizeof(float) : 0);
     const int gx = !CENTRE ? Q / 16 : Q == 16 ? 1 : Q / 32;                // tiles per run of hops
     const int gy = CENTRE && Q == 16 ? (n_runs + 1) / 2 : n_runs;          // (two runs per tile)
     cudaError_t e = cudaFuncSetAttribute(dec_inv_kernel<P, Q, CENTRE, ACCUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
