@@ -41,8 +41,8 @@ Commands (each after the same command had exited 0 without ncu in the same gpuru
 
 Workload of the first two: the bench plan (cfg 2: 65536 / 8192 / 1024 points) over a 600 s track (28.8 M stereo samples per
 launch), second pass captured.  Under ncu the launches are serialised and cold-cache: compare shares, not absolutes (bench, same
-code, 1-hour track: 13.8 ms per step = 2.29 ms per 600 s; sum of the eight launches below: {sum(times) / 1e3:.2f} ms; the dominant launch,
-`band_fused_kernel<1024>`, is {100 * times[-1] / sum(times):.0f} % of the step here and 4.6 / 13.8 = 33 % in the bench).
+code, 1-hour track: 13.6 ms per step = 2.27 ms per 600 s; sum of the eight launches below: {sum(times) / 1e3:.2f} ms; the dominant launch,
+`band_fused_kernel<1024>`, is {100 * times[-1] / sum(times):.0f} % of the step here and 4.62 / 13.6 = 34 % in the bench).
 
 ## One step of the bench plan, launch by launch
 
@@ -50,7 +50,7 @@ code, 1-hour track: 13.8 ms per step = 2.29 ms per 600 s; sum of the eight launc
 * `dec_fwd` / `dec_mask` / `dec_inv ... 0` (Ls + i Rs) / `dec_inv ... 1` (centre) are the decimated kernels of the two band-limited
   bands (upmix_dec.cuh); template arguments: P (points per decimated sequence), Q (sequences), centre, accumulating.  The
   65536-point band is the first of the plan and stores; the 8192-point band adds to the outputs: its previous sums come in
-  through `cp.async` (LDGSTS) into shared memory.
+  through `cp.async` (LDGSTS) into shared memory, requested one frame ahead (two buffers).
 * DRAM bytes per stereo sample of the whole step: {sum(per_kernel):.1f} B against 20 B compulsory (8 in + 12 out); round 1 moved ~243 B.  The
   65536-point band: {sum(per_kernel[0:4]):.1f} B (round 1: 180 B, its four-step scratch is gone), the 8192-point band {sum(per_kernel[4:7]):.1f} B and the 1024-point band
   {per_kernel[7]:.1f} B, 24 B of each being the read-modify-write of the outputs that the band-order sum costs.
