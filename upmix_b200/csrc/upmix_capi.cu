@@ -186,7 +186,7 @@ int pick_hops_per_run(const UpmixPlan* p, int n_fft, int64_t total_hops, int n_t
 // (waves of co-resident CTAs) x (frames per run), so the run length that minimises that product is taken: long runs for
 // an hour of audio (3 replayed frames in ~290), one or two hops per run for a few seconds of it (the GPU is not full
 // anyway and what counts is the length of the serial chain per CTA).
-int pick_dec_hops_per_run(const UpmixPlan* p, const BandDev& b, int64_t total_hops, int n_tracks, int ctas_per_run) {
+int pick_dec_hops_per_run(const UpmixPlan* p, const BandDev& b, int64_t total_hops, int n_tracks, int ctas_per_run, int min_run = 1) {
     static const int run_max = [] { const char* e = getenv("UPMIX_DEC_RUN_MAX"); return e ? std::max(1, atoi(e)) : 320; }();
     const int64_t slots = (int64_t)p->sm_count * (1024 / b.dec.P);
     int64_t best_r = 1, best_cost = INT64_MAX;
@@ -195,7 +195,12 @@ int pick_dec_hops_per_run(const UpmixPlan* p, const BandDev& b, int64_t total_ho
         const int64_t ctas = (ctas_per_run ? runs * ctas_per_run : (runs + 1) / 2) * n_tracks;
         return ((ctas + slots - 1) / slots) * (r + 3);
     };
-    for (int64_t r = 1; r <= std::min<int64_t>(run_max, total_hops); r++) {
+    // min_run: calls whose pipelines run side by side on the plan's streams (short inputs) share the GPU, so the replayed
+    // frames of one-hop runs are paid for by the other pipelines: runs of at least three hops there (measured, 10 s of the
+    // default six bands: 0.164 ms with one-hop runs, 0.143 / 0.142 / 0.145 / 0.148 with at least 2 / 3 / 4 / 6)
+    static const int run_min_env = [] { const char* e = getenv("UPMIX_DEC_RUN_MIN"); return e ? std::max(1, atoi(e)) : 0; }();
+    const int64_t run_min = run_min_env ? run_min_env : min_run;
+    for (int64_t r = std::min<int64_t>(run_min, total_hops); r <= std::min<int64_t>(run_max, total_hops); r++) {
         const int64_t c = cost_of(r);
         if (c < best_cost || (c == best_cost && r > best_r)) { best_cost = c; best_r = r; }      // ties: fewer, longer runs
     }
@@ -204,8 +209,13 @@ int pick_dec_hops_per_run(const UpmixPlan* p, const BandDev& b, int64_t total_ho
 
 // One decimated band over hops [a.hop_begin, a.hop_end) of every track, in waves: forward + mask of the wave's frames,
 // then the inverse / overlap-add of Ls + i Rs and of the centre.
-int run_dec_band(const UpmixPlan* p, const BandDev& b, const SegArgs& a, int n_tracks, char* scratch, const DecLayout& dl, cudaStream_t st) {
+// `side` (optional, with its event): a second stream for the centre's inverse, used when the band goes through in ONE wave
+// (short inputs, where the length of the serial chain is what counts; the next wave would overwrite the spectra).
+int run_dec_band(const UpmixPlan* p, const BandDev& b, const SegArgs& a, int n_tracks, char* scratch, const DecLayout& dl, cudaStream_t st,
+                 cudaStream_t side = nullptr, cudaEvent_t ev_side = nullptr, bool* side_used = nullptr, int min_run = 1) {
     const int64_t h_begin = a.hop_begin, h_end = a.hop_end;
+    if (dl.wave_tracks < n_tracks || h_end - h_begin > dl.wave_hops || a.fold) side = nullptr;
+    if (side_used) *side_used = side != nullptr && h_end > h_begin;
     for (int t0 = 0; t0 < n_tracks; t0 += dl.wave_tracks) {
         const int nt = std::min(dl.wave_tracks, n_tracks - t0);
         SegArgs at = a;
@@ -227,11 +237,15 @@ int run_dec_band(const UpmixPlan* p, const BandDev& b, const SegArgs& a, int n_t
             aw.hop_end = w1;
             CU_CHECK(launch_dec_fwd(b, aw, w, nt, st));
             const int groups = b.dec.Q / 16;
-            aw.hops_per_run = pick_dec_hops_per_run(p, b, w1 - w0, nt, groups);
+            if (!a.fold && side) {
+                CU_CHECK(cudaEventRecord(ev_side, st));
+                CU_CHECK(cudaStreamWaitEvent(side, ev_side, 0));
+            }
+            aw.hops_per_run = pick_dec_hops_per_run(p, b, w1 - w0, nt, groups, min_run);
             CU_CHECK(launch_dec_inv(b, aw, w, (int)((w1 - w0 + aw.hops_per_run - 1) / aw.hops_per_run), nt, false, st));
             if (!a.fold) {
-                aw.hops_per_run = pick_dec_hops_per_run(p, b, w1 - w0, nt, groups / 2);
-                CU_CHECK(launch_dec_inv(b, aw, w, (int)((w1 - w0 + aw.hops_per_run - 1) / aw.hops_per_run), nt, true, st));
+                aw.hops_per_run = pick_dec_hops_per_run(p, b, w1 - w0, nt, groups / 2, min_run);
+                CU_CHECK(launch_dec_inv(b, aw, w, (int)((w1 - w0 + aw.hops_per_run - 1) / aw.hops_per_run), nt, true, side ? side : st));
             }
         }
     }
@@ -260,7 +274,7 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
     // (block streaming forks too: every band has its own ring and its own output slot)
     const bool fork = p->multi_stream && nb > 1 && !direct;
     bool first = true;
-    bool used[UpmixPlan::N_AUX] = {false, false, false};
+    bool used[UpmixPlan::N_AUX] = {};
     int next_fused = 1;
     int64_t dec_off = lay.dec_off;
     if (fork) CU_CHECK(cudaEventRecord(p->ev_fork, caller));
@@ -268,14 +282,16 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
     for (int bi = 0; bi < nb; bi++) {
         const BandDev& b = p->bands[bi];
         const bool dec = b.dec.P != 0 && band_state == nullptr;
+        int side_si = -1;
         const DecLayout dlay = b.dec.P ? make_dec_layout(b, seg_len, n_tracks) : DecLayout();
         char* dec_scratch = reinterpret_cast<char*>(workspace) + dec_off;
         dec_off += dlay.total;
         if (fork) {
             const bool own = b.n_fft <= FUSED_MAX_N || dec;     // four-step bands share one scratch, hence one stream
             const int si = own ? next_fused : 0;
-            if (own) next_fused = next_fused == UpmixPlan::N_AUX - 1 ? 1 : next_fused + 1;
+            if (own) next_fused = next_fused == UpmixPlan::N_MAIN ? 1 : next_fused + 1;
             st = p->aux[si];
+            side_si = own && dec ? si + UpmixPlan::N_MAIN : -1;
             if (!used[si]) {
                 CU_CHECK(cudaStreamWaitEvent(st, p->ev_fork, 0));
                 used[si] = true;
@@ -321,8 +337,12 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
         a.hop_end = (a.seg_end + b.hop - 1) / b.hop;
         const int64_t total_hops = a.hop_end - a.hop_begin;
         if (dec) {
-            const int rc = run_dec_band(p, b, a, n_tracks, dec_scratch, dlay, st);
+            const bool two = fork && side_si > 0 && !a.fold;
+            bool side_used = false;
+            const int rc = run_dec_band(p, b, a, n_tracks, dec_scratch, dlay, st, two ? p->aux[side_si] : nullptr, two ? p->ev_side[side_si] : nullptr,
+                                        &side_used, fork ? 3 : 1);
             if (rc) return rc;
+            if (side_used) used[side_si] = true;
         } else if (b.fb.tw_full && !a.state && !a.mix) {
             // dense band of 256 / 512 / 1024 points: 16 frames per tile; a run of r hops costs ceil((r + 3) / 16) tiles
             const int64_t slots = (int64_t)p->sm_count * fb_ctas_per_sm(b.n_fft);
@@ -672,7 +692,8 @@ int upmix_plan_create_ex(int n_bands, const UpmixBandDesc* bands, int out_mode, 
         bool ok = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) == cudaSuccess;
         for (int si = 0; si < UpmixPlan::N_AUX && ok; si++)
             ok = cudaStreamCreateWithFlags(&p->aux[si], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&p->ev_join[si], cudaEventDisableTiming) == cudaSuccess;
+                 cudaEventCreateWithFlags(&p->ev_join[si], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p->ev_side[si], cudaEventDisableTiming) == cudaSuccess;
         if (!ok) p->multi_stream = false;
         const char* eg = getenv("UPMIX_GRAPHS");
         p->use_graphs = !(eg && atoi(eg) == 0);
@@ -694,6 +715,7 @@ int upmix_plan_destroy(UpmixPlan* plan) {
     for (int si = 0; si < UpmixPlan::N_AUX; si++) {
         if (plan->aux[si]) cudaStreamDestroy(plan->aux[si]);
         if (plan->ev_join[si]) cudaEventDestroy(plan->ev_join[si]);
+        if (plan->ev_side[si]) cudaEventDestroy(plan->ev_side[si]);
     }
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     for (UpmixPlan::GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
@@ -943,7 +965,13 @@ int upmix_stream_block(const UpmixPlan* plan, void* state, int64_t samples_done,
     // graph nodes get the new pointers (cudaGraphExecKernelNodeSetParams) before the replay.
     UpmixPlan* mp = const_cast<UpmixPlan*>(plan);
     const int64_t pos = samples_done >= 2 * n_max ? 2 * n_max + samples_done % n_max : samples_done;
-    if (mp->use_graphs && mp->cap_stream && samples_done >= 2 * n_max && n_new <= 65536 && plan->delay <= 65536) {
+    // (blocks much shorter than the largest STFT would need more graphs than the cache holds: they take the plain path)
+    int64_t gcd_a = n_max, gcd_b = n_new;
+    while (gcd_b) { const int64_t t = gcd_a % gcd_b; gcd_a = gcd_b; gcd_b = t; }
+    const int64_t phases = n_max / gcd_a;
+    constexpr size_t STREAM_GRAPHS_MAX = 32;
+    if (mp->use_graphs && mp->cap_stream && samples_done >= 2 * n_max && n_new <= 65536 && plan->delay <= 65536 &&
+        phases <= (int64_t)STREAM_GRAPHS_MAX) {
         const uint64_t align16 = ((reinterpret_cast<uintptr_t>(out_l) | reinterpret_cast<uintptr_t>(out_r) | reinterpret_cast<uintptr_t>(out_c)) & 15) == 0;
         uint64_t key[16] = {(uint64_t)(uintptr_t)state, (uint64_t)pos, (uint64_t)n_new, (uint64_t)n_tracks, (uint64_t)in_stride, (uint64_t)out_stride,
                             (uint64_t)(uintptr_t)workspace, (uint64_t)workspace_bytes, align16, out_c ? 1u : 0u, 0, 0, 0, 0, 0, 0x5354524dull /* "STRM" */};
@@ -1000,7 +1028,7 @@ int upmix_stream_block(const UpmixPlan* plan, void* state, int64_t samples_done,
                 g.io[0] = in_l; g.io[1] = in_r; g.io[2] = out_c; g.io[3] = out_l; g.io[4] = out_r;
                 g.n_kernels = (int)(launch_count(false) - before);
                 g.last_use = ++mp->graph_clock;
-                if (mp->stream_graphs.size() >= 16) {          // evict the least recently used
+                if (mp->stream_graphs.size() >= STREAM_GRAPHS_MAX) {          // evict the least recently used
                     size_t lru = 0;
                     for (size_t i = 1; i < mp->stream_graphs.size(); i++)
                         if (mp->stream_graphs[i].last_use < mp->stream_graphs[lru].last_use) lru = i;

@@ -26,10 +26,14 @@ struct UpmixPlan {
     // (forked from / joined to the caller's stream with events): co-resident CTAs of different pipelines
     // fill each other's stalls and launch tails.  Pipelines of the four-step path share one scratch and
     // therefore one stream.
-    static constexpr int N_AUX = 3;
-    cudaStream_t aux[N_AUX] = {nullptr, nullptr, nullptr};
+    // aux[0]: four-step pipelines; aux[1 .. N_MAIN]: fused / decimated pipelines, round robin; aux[si + N_MAIN]: the centre's
+    // inverse of the decimated pipeline on aux[si] (it only shares the masked spectra with the inverse of Ls + i Rs)
+    static constexpr int N_MAIN = 4;
+    static constexpr int N_AUX = 1 + 2 * N_MAIN;
+    cudaStream_t aux[N_AUX] = {};
     cudaEvent_t ev_fork = nullptr;
-    cudaEvent_t ev_join[N_AUX] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_join[N_AUX] = {};
+    cudaEvent_t ev_side[N_AUX] = {};   // forward + mask of a decimated pipeline done: its centre stream may start
     bool multi_stream = false;
     UpmixHostCtx* host = nullptr;   // buffers of upmix_process_host_ex, created on first use
     // Short calls (the staged band sum: a few seconds of audio, 10-20 launches on four streams) are captured once into
