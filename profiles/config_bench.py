@@ -79,14 +79,14 @@ report("cfg5 shape: 32 x 5-min tracks, 6 bands", e1, ce.plan_for(e1), 32, 300, 4
 # Bela streaming latency: wall time per 2048-sample hardware block
 up = bela.MultiBandUpmix()
 quiet(up.setup, 2048, 48000.0, 4, [0.0, 500.0, 2000.0, 8000.0, 24000.0])
-L, R = synth(1, 2048 * 64, 2)
+L, R = synth(1, 2048 * 96, 2)
 import time
-for i in range(8):
+for i in range(32):                      # (start-up blocks, then one graph capture per block phase)
     up.process(L[0, i * 2048:(i + 1) * 2048], R[0, i * 2048:(i + 1) * 2048])
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-for i in range(8, 64):
+for i in range(32, 96):
     up.process(L[0, i * 2048:(i + 1) * 2048], R[0, i * 2048:(i + 1) * 2048])
 torch.cuda.synchronize()
-dt = (time.perf_counter() - t0) / 56
+dt = (time.perf_counter() - t0) / 64
 print(f"cfg3 streaming: {dt * 1e6:.0f} us wall per 2048-sample block (42.7 ms of audio; algorithmic latency 3*2048 samples = 128 ms)")
