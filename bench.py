@@ -481,20 +481,23 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": audio_seconds_total / float(tt.item()), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": float(tt.item()) * 1e3, "api": e2e_api}
-        # bare copies of the same bytes (pinned, both directions at once on two streams): the ceiling of this box
+        # bare copies of the same bytes (pinned, both directions at once on two streams): the ceiling of this box.  The two
+        # directions move DIFFERENT amounts (8 B up, 12 B down per stereo sample) and slow each other while both are busy
+        # (~47 GB/s each against ~54 alone), so the ceiling copies the exact bytes in the exact ratio: `pieces` copies per
+        # direction, sized n_in / pieces and n_o / pieces floats, at most 1 GiB each
         n_in, n_o = h2d // 4, d2h // 4
-        cap = 1 << 28                                                    # floats per staging buffer (1 GiB)
-        hb_in = torch.empty(min(n_in, cap), dtype=torch.float32, pin_memory=True)
-        hb_out = torch.empty(min(n_o, cap), dtype=torch.float32, pin_memory=True)
+        pieces = max(1, -(-n_o // (1 << 28)))
+        p_in, p_o = -(-n_in // pieces), -(-n_o // pieces)
+        hb_in = torch.empty(p_in, dtype=torch.float32, pin_memory=True)
+        hb_out = torch.empty(p_o, dtype=torch.float32, pin_memory=True)
         db_in, db_out = torch.empty_like(hb_in, device=dev), torch.empty_like(hb_out, device=dev)
         s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
         def copies():
-            with torch.cuda.stream(s1):
-                for _ in range(-(-n_in // hb_in.numel())):
+            for _ in range(pieces):
+                with torch.cuda.stream(s1):
                     db_in.copy_(hb_in, non_blocking=True)
-            with torch.cuda.stream(s2):
-                for _ in range(-(-n_o // hb_out.numel())):
+                with torch.cuda.stream(s2):
                     hb_out.copy_(db_out, non_blocking=True)
             s1.synchronize()
             s2.synchronize()
@@ -504,13 +507,14 @@ def main():
         for _ in range(reps):
             copies()
         dtc = (time.perf_counter() - t0) / reps
-        moved = (-(-n_in // hb_in.numel())) * hb_in.numel() * 4 + (-(-n_o // hb_out.numel())) * hb_out.numel() * 4
-        dtc *= (h2d + d2h) / moved                                       # whole buffers were copied: scale to the exact byte count
+        moved = pieces * (p_in + p_o) * 4
+        dtc *= (h2d + d2h) / moved                                       # (rounding of the piece sizes: < 1e-6)
         tc = torch.tensor([dtc], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tc, op=dist.ReduceOp.MAX)
         e2e["copy_ceiling"] = {"ms_per_step": float(tc.item()) * 1e3, "frac": float(tc.item()) / float(tt.item()),
-                               "what": "bare pinned H2D + D2H of the same bytes, two streams, all ranks at once, max over ranks"}
+                               "what": "bare pinned H2D + D2H of exactly the same bytes (8 B up, 12 B down per stereo sample), two streams, "
+                                       "all ranks at once, max over ranks"}
         del hb_in, hb_out, db_in, db_out
         # the call exactly as main.py makes it: float64 strided views of an interleaved pageable array (rank 0 only)
         if rank == 0 and args.workload != "cfg5" and not args.split_track:

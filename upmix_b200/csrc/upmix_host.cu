@@ -177,14 +177,18 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
         // UPMIX_HOST_SEG (samples): fixed segment length, for tests and sweeps
         const char* ev = getenv("UPMIX_HOST_SEG");
         const int64_t forced = ev ? std::max<int64_t>(1, atoll(ev)) : 0;
-        const int64_t n_seg = std::max<int64_t>(1, std::min<int64_t>(64, (n + MAX_SEG / 2) / MAX_SEG));
+        const char* eg = getenv("UPMIX_HOST_GROWTH");              // segment i + 1 = growth x segment i, for sweeps
+        const double growth = eg ? std::max(1.05, atof(eg)) : 2.0;
+        const char* em = getenv("UPMIX_HOST_MAXSEG");              // (samples) longest segment, for sweeps
+        const int64_t max_seg_len = em ? std::max<int64_t>(FIRST_SEG, atoll(em)) : MAX_SEG;
+        const int64_t n_seg = std::max<int64_t>(1, std::min<int64_t>(64, (n + max_seg_len / 2) / max_seg_len));
         const int64_t seg = round_up(forced ? forced : (n + n_seg - 1) / n_seg, align);
         int64_t step = forced ? seg : std::min(seg, round_up(FIRST_SEG, align));
         int64_t pos = 0;
         while (pos < n) {
             pos = std::min(n, pos + step);
             bounds.push_back(pos);
-            step = std::min(seg, 2 * step);
+            step = std::min(seg, round_up((int64_t)(growth * (double)step), align));
         }
     }
     const int n_segs = (int)bounds.size() - 1;
@@ -240,7 +244,28 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
         HOST_CHECK(cudaStreamCreateWithFlags(&c.s_main, cudaStreamNonBlocking));
         HOST_CHECK(cudaStreamCreateWithFlags(&c.s_down, cudaStreamNonBlocking));
     }
-    const int n_up = std::max(n_chunks, n_segs);              // ev_up: per chunk (staged input) or per segment (pinned input)
+    // pinned float32 input goes up in place, one piece per segment: what the segment adds to the uploaded range.
+    // (UPMIX_HOST_H2D_AHEAD=1 uploads in pieces of its own -- short first, doubling up to 32 MB per channel -- so that the
+    // upload runs ahead at full speed whatever the segment lengths are.  Measured, same call, three times each: 43.4-44.1 ms
+    // against 41.8-42.3 ms: with both directions busy each moves ~47 GB/s instead of ~54, and the download -- 1.5x the
+    // bytes -- is the one that must not be slowed; an upload paced by the segments leaves it more of the link.)
+    std::vector<int64_t> h2d_bounds(1, 0);
+    static const bool h2d_ahead = [] { const char* e = getenv("UPMIX_HOST_H2D_AHEAD"); return e && atoi(e) != 0; }();
+    if (in_direct && h2d_ahead) {
+        int64_t step = std::min<int64_t>(n, FIRST_SEG + plan->halo), pos = 0;
+        while (pos < n) {
+            pos = std::min(n, pos + step);
+            h2d_bounds.push_back(pos);
+            step = std::min<int64_t>(8 << 20, 2 * step);
+        }
+    } else if (in_direct) {                                       // one piece per segment: what the segment adds
+        for (int i = 0; i < n_segs; i++) {
+            const int64_t need = std::min(n, bounds[i + 1] + plan->halo);
+            if (need > h2d_bounds.back()) h2d_bounds.push_back(need);
+        }
+    }
+    const int n_h2d = (int)h2d_bounds.size() - 1;
+    const int n_up = std::max(std::max(n_chunks, n_segs), n_h2d);   // ev_up: per chunk (staged input) or per piece (pinned input)
     const size_t n_events = (size_t)n_up + n_segs + n_pieces;
     while (c.events.size() < n_events) {
         cudaEvent_t e;
@@ -336,19 +361,26 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
     // ---- caller thread: segments ----
     int rc = UPMIX_OK;
     int next_chunk = 0, next_piece = 0;
-    int64_t uploaded = 0;
+    int up_piece = 0, up_waited = 0;
     for (int i = 0; i < n_segs && rc == UPMIX_OK && !err.load(); i++) {
         const int64_t a = bounds[i], b = bounds[i + 1];
         const int64_t need = std::min(n, b + plan->halo);
         if (in_direct) {
-            if (uploaded < need) {
-                const size_t bytes = (size_t)(need - uploaded) * sizeof(float);
-                cudaError_t e = cudaMemcpyAsync(d_l + uploaded, (const float*)L + uploaded, bytes, cudaMemcpyHostToDevice, c.s_up);
-                if (e == cudaSuccess) e = cudaMemcpyAsync(d_r + uploaded, (const float*)R + uploaded, bytes, cudaMemcpyHostToDevice, c.s_up);
-                if (e == cudaSuccess) e = cudaEventRecord(ev_up[i], c.s_up);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(c.s_main, ev_up[i], 0);
+            if (i == 0) {                                          // queue the whole upload, piece by piece
+                cudaError_t e = cudaSuccess;
+                for (int k = 0; k < n_h2d && e == cudaSuccess; k++) {
+                    const int64_t p0 = h2d_bounds[k];
+                    const size_t bytes = (size_t)(h2d_bounds[k + 1] - p0) * sizeof(float);
+                    e = cudaMemcpyAsync(d_l + p0, (const float*)L + p0, bytes, cudaMemcpyHostToDevice, c.s_up);
+                    if (e == cudaSuccess) e = cudaMemcpyAsync(d_r + p0, (const float*)R + p0, bytes, cudaMemcpyHostToDevice, c.s_up);
+                    if (e == cudaSuccess) e = cudaEventRecord(ev_up[k], c.s_up);
+                }
                 if (e != cudaSuccess) { err.store(1); break; }
-                uploaded = need;
+            }
+            while (up_piece < n_h2d && h2d_bounds[up_piece] < need) up_piece++;       // pieces 0 .. up_piece - 1 cover [0, need)
+            if (up_piece > up_waited) {
+                if (cudaStreamWaitEvent(c.s_main, ev_up[up_piece - 1], 0) != cudaSuccess) { err.store(1); break; }
+                up_waited = up_piece;
             }
         } else {
             const int last = (int)((need - 1) / chunk);
@@ -358,6 +390,9 @@ int upmix_process_host_ex(const UpmixPlan* cplan, const void* L, const void* R, 
             }
         }
         if (err.load()) break;
+        // UPMIX_HOST_NOCOMPUTE=1 (measurement only): the copy pipeline without the kernels -- outputs are whatever the buffer holds
+        static const bool no_compute = [] { const char* e = getenv("UPMIX_HOST_NOCOMPUTE"); return e && atoi(e) != 0; }();
+        if (!no_compute)
         rc = upmix_process_segment(plan, d_l, d_r, 0, n, n, a, b, 1, c.cap, d_o[0] ? d_o[0] + a : nullptr, d_o[1] + a, d_o[2] + a,
                                    c.cap, c.ws, c.ws_bytes, c.s_main);
         if (rc != UPMIX_OK) break;
