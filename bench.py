@@ -584,6 +584,10 @@ def main():
                              "achieved": dom_tflops, "frac": dom_tflops / fp32_tflops, "traffic": traffic, "traffic_note": traffic_note,
                              "algorithmic": f"10*T*log2(N) = {10 * T_REAL_FFTS * math.log2(dom_n):.0f} flops per stereo sample for this band "
                                             f"(T={T_REAL_FFTS} real FFTs/frame, 75% overlap), {n} samples per launch; 20 B/sample compulsory HBM bytes",
+                             "note": "round 1's dominant launch, band_fused_kernel<8192> (5.64 ms, 0.275), no longer runs: the 8192- and "
+                                     "65536-point bands take the decimated kernels (band_tflops_nominal below: they do less than the nominal "
+                                     "work); this launch took 4.7 ms (0.25) in round 1.  FP32-pipe utilisation, instruction mix and the "
+                                     "shared-memory wavefront budget that bound it: profiles/r02_ncu_summary.md, profiles/r02_tuning.md",
                              "band_ms": dict(zip([str(s) for s in sizes], band_ms)),
                              "band_tflops_nominal": {str(s): 10 * T_REAL_FFTS * math.log2(s) * n / (m * 1e-3) / 1e12 for s, m in zip(sizes, band_ms)}})
         else:
