@@ -503,7 +503,10 @@ int upmix_plan_create_ex(int n_bands, const UpmixBandDesc* bands, int out_mode, 
     }
     // the fold-down epilogue of a plan with four-step bands is applied by the band kernels' copy-out, which the
     // decimated kernels do not have: such plans keep the older paths
-    if (out_mode == UPMIX_OUT_FOLD && any_four_step) std::fill(dec_p.begin(), dec_p.end(), 0);
+    if (out_mode == UPMIX_OUT_FOLD && any_four_step) {
+        std::fill(dec_p.begin(), dec_p.end(), 0);
+        use_fb = false;      // (the frame-batched kernel has no fold-down epilogue either: staged and direct sums must pick the same kernels)
+    }
     int64_t floats = 0;
     for (size_t gi = 0; gi < groups.size(); gi++) {
         const auto& grp = groups[gi];
