@@ -525,6 +525,49 @@ def test_stream_graph_replay_and_split_runs_are_bit_identical(ce):
             assert torch.equal(outs[1][ch][d:], off[ch][:n - d])
 
 
+def test_repeated_runs_are_bit_identical(ce):
+    """compute-sanitizer's racecheck is closed on this pool, so races are looked for by their symptom: a kernel with a
+    shared-memory race (a missing barrier between passes, a tile read before its cp.async / TMA copy landed, an overlap-add
+    carry taken from the wrong tile) gives results that change from run to run or with what else is resident.  Every kernel
+    family -- decimated, frame-batched, one-frame, four-step, band sum, with and without accumulation -- runs the same input
+    eight times, alone and with a second plan busy on another stream, and must return the same bits."""
+    import torch
+    sr = 48000
+    L, R = uo.synth_stereo(25 * sr + 123, 5, stress=True)
+    dl, dr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    noise = torch.randn(2, 40 * sr, device="cuda")
+    other = ce.plan_for(quiet(ce.chain_bands, [0, 900, 5000], 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=4096))
+    side = torch.cuda.Stream()
+    cases = [([0, 200, 2000], 65536, {}), ([0, 30, 120, 480, 1920, 7680], 65536, {}), ([0, 400, 4000], 16384, {"UPMIX_DEC": "0"}),
+             ([0, 1000, 6000], 2048, {"UPMIX_FB": "0"})]
+    for edges, max_block, env in cases:
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            ext = quiet(ce.chain_bands, edges, 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=max_block)
+            from upmix_b200 import _native
+            plan = _native.Plan([b.plan_tables() for b in ext], _native.OUT_LSCRS)
+            for direct_min in ("1", str(1 << 60)):                 # pipelines adding into the outputs / per-band slots + band sum
+                os.environ["UPMIX_DIRECT_MIN"] = direct_min
+                ref = None
+                for rep in range(8):
+                    if rep % 2:
+                        with torch.cuda.stream(side):
+                            other.process(noise[0], noise[1])
+                    got = torch.stack(plan.process(dl, dr))
+                    if ref is None:
+                        ref = got.clone()
+                    assert torch.equal(ref, got), (edges, direct_min, rep)
+                torch.cuda.synchronize()
+        finally:
+            os.environ.pop("UPMIX_DIRECT_MIN", None)
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+
 def test_pcm16_edge_kernels(ce):
     """WAV edge on the device: int16 stereo -> planar float32 + peak, float32 stereo -> int16."""
     import torch
