@@ -133,6 +133,30 @@ def test_every_size_vs_oracle(ce, n_fft):
     print(n_fft, [(nm, round(s, 1), er) for nm, s, er in rep])
 
 
+@pytest.mark.parametrize("overlap", [0.5, 0.875])
+def test_other_overlaps_vs_oracle(ce, overlap):
+    """chain_bands takes any overlap (center_extraction.py:518-580; main.py fixes 0.75).  50 % and 87.5 % on bands up to
+    8192 points run in the one-frame kernel; 50 % on larger bands runs on the 75 % kernels (decimated / four-step) with
+    every other frame absent -- the odd frames add exact zeros, so the sum is the reference's two-frame overlap-add."""
+    sr = 48000
+    edges, max_block = ([0, 30, 120, 480, 1920, 7680], 65536) if overlap == 0.5 else ([0, 500, 2000, 8000], 8192)
+    ext = quiet(ce.chain_bands, edges, overlap, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=max_block)
+    bands = uo.chain(edges, overlap, uo.blackman_harris, sr, max_block=max_block)
+    assert [e.hop_size for e in ext] == [b.hop for b in bands]
+    n = 5 * sr + 4321
+    L, R = uo.synth_stereo(n, 17, stress=True)
+    got = ce.extract_center_left_right_multi_band_in_memory(L, R, sr, ext)
+    ref = uo.upmix_multiband(bands, L.astype(np.float64), R.astype(np.float64))
+    peak = float(max(np.abs(L).max(), np.abs(R).max()))
+    assert_parity(ref, got, peak, what=f"overlap {overlap}")
+    if overlap == 0.5:
+        # a dense band above 8192 points takes the four-step kernels
+        e = ce.MultiBandExtractorAccu(16384, 0.5, ce.make_blackman_harris, 100.0, 20000.0, sr, "raised_cosine", 25.0, 0.0)
+        b = uo.make_band(16384, 0.5, uo.blackman_harris, 100.0, 20000.0, sr, "raised_cosine", 25.0, 0.0)
+        ref1 = uo.process_band_batched(b, L.astype(np.float64), R.astype(np.float64))
+        assert_parity(ref1, e.process_all_blocks(L, R), peak, what="dense 16384, overlap 0.5")
+
+
 @pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 255, 1000, 4097])
 def test_ragged_and_tiny_lengths(ce, n):
     sr = 48000

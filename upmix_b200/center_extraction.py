@@ -316,8 +316,8 @@ def _check_supported(band_extractors: Sequence[MultiBandExtractorAccu]) -> None:
                 "the CUDA path implements the sizes the dynamic-resolution rule produces and has no CPU fallback")
         if n % h or h % 2:
             raise NotImplementedError(f"band {i}: hop_size={h} must be even and divide block_size={n}")
-        if n > _native.FUSED_MAX_N and 4 * h != n:
-            raise NotImplementedError(f"band {i}: block_size={n} > {_native.FUSED_MAX_N} needs 75 % overlap")
+        if n > _native.FUSED_MAX_N and 4 * h != n and 2 * h != n:
+            raise NotImplementedError(f"band {i}: block_size={n} > {_native.FUSED_MAX_N} needs 75 % or 50 % overlap")
 
 
 _PLAN_CACHE: "list" = []      # [(key, plan)], most recent last

@@ -461,9 +461,13 @@ int upmix_plan_create_ex(int n_bands, const UpmixBandDesc* bands, int out_mode, 
             return fail(UPMIX_E_UNSUPPORTED, "band %d: n_fft=%d is not a power of two in [64, %d]", i, d.n_fft, LARGE_MAX_N);
         if (d.hop < 2 || d.n_fft % d.hop != 0 || (d.hop & 1))
             return fail(UPMIX_E_UNSUPPORTED, "band %d: hop=%d must be even and divide n_fft=%d", i, d.hop, d.n_fft);
-        if (d.n_fft > FUSED_MAX_N && d.hop * 4 != d.n_fft)
-            return fail(UPMIX_E_UNSUPPORTED, "band %d: n_fft=%d > %d requires hop = n_fft/4 (75%% overlap), got %d", i, d.n_fft, FUSED_MAX_N, d.hop);
+        if (d.n_fft > FUSED_MAX_N && d.hop * 4 != d.n_fft && d.hop * 2 != d.n_fft)
+            return fail(UPMIX_E_UNSUPPORTED, "band %d: n_fft=%d > %d requires hop = n_fft/4 or n_fft/2 (75%% / 50%% overlap), got %d", i, d.n_fft,
+                        FUSED_MAX_N, d.hop);
     }
+    // hop the kernels step by / frame step (BandDev::hop): 50 % overlap above 8192 points runs as 75 % with every other frame absent
+    auto khop = [](const UpmixBandDesc& d) { return d.n_fft > FUSED_MAX_N && d.hop * 2 == d.n_fft ? d.n_fft / 4 : d.hop; };
+    auto kstep = [](const UpmixBandDesc& d) { return d.n_fft > FUSED_MAX_N && d.hop * 2 == d.n_fft ? 2 : 1; };
     // Bands whose STFT is identical (size, hop, both windows) run as ONE pipeline: they share the forward
     // transform, get their own mask per bin, and -- inverse transform and overlap-add being linear -- share
     // the inverse as well.  groups[g] = indices of the bands of pipeline g, in list order.
@@ -498,7 +502,7 @@ int upmix_plan_create_ex(int n_bands, const UpmixBandDesc* bands, int out_mode, 
                 if (bands[m].gain[k] != 0.f) { top = k; break; }
         dec_k[gi] = top;
         const int P = top < 128 ? 128 : top < 256 ? 256 : top < 512 ? 512 : 0;
-        if (use_dec && P && d.hop * 4 == d.n_fft && d.n_fft >= 16 * P) dec_p[gi] = P;
+        if (use_dec && P && khop(d) * 4 == d.n_fft && d.n_fft >= 16 * P) dec_p[gi] = P;
         if (d.n_fft > FUSED_MAX_N && !dec_p[gi]) any_four_step = true;
     }
     // the fold-down epilogue of a plan with four-step bands is applied by the band kernels' copy-out, which the
@@ -618,7 +622,8 @@ int upmix_plan_create_ex(int n_bands, const UpmixBandDesc* bands, int out_mode, 
             }
         }
         b.n_fft = d.n_fft;
-        b.hop = d.hop;
+        b.hop = khop(d);
+        b.frame_step = kstep(d);
         b.tw_fft = b.tw_inv = b.tw_half = b.tw_pack = b.tw_col = nullptr;
         memcpy(&host[off], d.ana, sizeof(float) * d.n_fft);      // ana[n_fft] = 0 follows (host is zero-filled)
         b.ana = dbase + off;
@@ -1064,6 +1069,7 @@ int upmix_frame_step(const UpmixPlan* plan, void* ring, int64_t frame_index, con
     if (frame_index < 0) return fail(UPMIX_E_INVALID, "negative frame index");
     DeviceGuard guard(plan->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (b.frame_step > 1) return fail(UPMIX_E_UNSUPPORTED, "frame stepping above %d points needs 75%% overlap", FUSED_MAX_N);
     if (b.n_fft > FUSED_MAX_N) {
         // four-step path: the frame is slot 0 of a two-frame wave, its partner slot is zero
         const Layout lay = make_layout(plan, b.hop, n_tracks, false, true);

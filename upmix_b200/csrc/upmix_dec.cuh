@@ -80,6 +80,19 @@ __global__ void __launch_bounds__(P / 2, 1024 / P) dec_fwd_kernel(const BandDev 
     const float* __restrict__ inr = a.in_r + (long long)track * a.in_stride;
     const float* __restrict__ ana = b.ana;
 
+    if (b.frame_step > 1 && (w.frame0 + fl) % b.frame_step != 0) {
+        // 50 % overlap run on the 75 % machinery: this frame does not exist -- its live bins are zero
+        const float2 zero = make_float2(0.f, 0.f);
+        if constexpr (FUSE_MASK) {
+            float2* __restrict__ sp = w.spec + (((long long)track * w.n_frames + fl) * 3) * KP;
+            for (int k = tid; k <= K; k += T) sp[k] = sp[KP + k] = sp[2 * KP + k] = zero;
+        } else {
+            float2* __restrict__ pz = w.part + (((long long)track * w.n_frames + fl) * (Q / 16) + g) * 2 * KP;
+            for (int k = tid; k <= K; k += T) pz[k] = pz[KP + k] = zero;
+        }
+        return;
+    }
+
     // pass 0 (radix R0, no twiddles): input point idx of sequence q is sample Q*idx + q of the frame
     {
         float2 v[IT0][R0];

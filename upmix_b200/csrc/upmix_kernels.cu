@@ -51,7 +51,11 @@ __global__ void __launch_bounds__(128) col_fwd_kernel(const BandDev b, const Seg
     float2 v[COL_R];
     const float* __restrict__ pl = inl + (s0 - a.in_begin);
     const float* __restrict__ pr = inr + (s0 - a.in_begin);
-    if (s0 >= a.in_begin && s0 + b.n_fft <= a.in_end) {          // whole frame available (block-uniform)
+    if (b.frame_step > 1 && f % b.frame_step != 0) {
+        // 50 % overlap run on the 75 % machinery: this frame does not exist -- zero spectrum
+#pragma unroll
+        for (int r = 0; r < COL_R; r++) v[r] = make_float2(0.f, 0.f);
+    } else if (s0 >= a.in_begin && s0 + b.n_fft <= a.in_end) {          // whole frame available (block-uniform)
 #pragma unroll
         for (int r = 0; r < COL_R; r++) {
             const int n = r * N2 + n2;

@@ -33,7 +33,11 @@ struct FbDev {
 // Device tables of one band (all in global memory, read-only during processing).
 struct BandDev {
     int n_fft;
-    int hop;
+    int hop;                   // hop the kernels step by.  A band above 8192 points with 50 % overlap (hop = n_fft/2) runs on
+                               // the 75 % machinery: hop = n_fft/4 here and frame_step = 2 -- the odd frames do not exist
+                               // (their spectra are zero: they add exact zeros to the overlap-add, so the result is the
+                               // two-frame sum of center_extraction.py:392-407 bit for bit)
+    int frame_step;            // 1, or 2 (see hop)
     const float* ana;          // [n_fft + 1]   analysis window, followed by one zero
     const float* syn;          // [n_fft]       synthesis window / n_fft (the inverse FFT is unnormalised)
     const float* gain;         // [n_gains][gain_stride] band-limit gains of the bands merged into this
