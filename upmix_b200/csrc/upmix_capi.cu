@@ -344,16 +344,17 @@ int run_segment(const UpmixPlan* p, const float* L, const float* R, int64_t in_b
             if (rc) return rc;
             if (side_used) used[side_si] = true;
         } else if (b.fb.tw_full && !a.state && !a.mix) {
-            // dense band of 256 / 512 / 1024 points: 16 frames per tile; a run of r hops costs ceil((r + 3) / 16) tiles
+            // dense band of 256 / 512 / 1024 points: FT frames per tile; a run of r hops costs ceil((r + 3) / FT) tiles
             const int64_t slots = (int64_t)p->sm_count * fb_ctas_per_sm(b.n_fft);
+            const int64_t FT = fb_frames_per_tile(b.n_fft);
             int64_t best_k = 1, best_cost = INT64_MAX;
-            for (int64_t k = 1; k <= 64; k++) {
-                const int64_t r = 16 * k - 3, runs = (total_hops + r - 1) / r;
+            for (int64_t k = 1; k <= 1024 / FT; k++) {
+                const int64_t r = FT * k - 3, runs = (total_hops + r - 1) / r;
                 const int64_t cost = ((runs * n_tracks + slots - 1) / slots) * k;
                 if (cost < best_cost || (cost == best_cost && runs * n_tracks > slots / 2)) { best_cost = cost; best_k = k; }
                 if (runs == 1) break;
             }
-            a.hops_per_run = (int)(16 * best_k - 3);
+            a.hops_per_run = (int)(FT * best_k - 3);
             const int n_runs = (int)((total_hops + a.hops_per_run - 1) / a.hops_per_run);
             CU_CHECK(launch_band_fb(b, a, n_runs, n_tracks, st));
         } else if (b.n_fft <= FUSED_MAX_N) {

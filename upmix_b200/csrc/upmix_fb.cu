@@ -12,10 +12,9 @@ unsigned long long& launch_counter();
 // builds the twiddle tables from them); 0: size not served by the frame-batched kernel
 void fb_plan(int n_fft, int* ra, int* rb, int* ha) {
     *ra = *rb = *ha = 0;
-    // Measured on B200, ms per band-hour of a dense band, frame-batched / one frame per CTA: 256 points 3.90 / 5.66, 512
-    // 4.30 / 5.00, 1024 6.02 / 4.84 -- a 1024-point tile of 16 frames needs 209 KB of shared memory (one CTA of 512
-    // threads per SM, 128 registers, half of them idle in the centre's radix-32 pass), so 1024 points keep the one-frame
-    // kernel unless UPMIX_FB_MAX_N says otherwise.
+    // Measured on B200, ms per band-hour of a dense band, frame-batched / one frame per CTA: 256 points 3.71 / 5.65, 512
+    // 4.11 / 5.01, 1024 4.71 (8-frame tiles, two CTAs per SM; 5.05 with 16-frame tiles, one CTA of 512 threads) / 4.60 --
+    // so 1024 points keep the one-frame kernel unless UPMIX_FB_MAX_N says otherwise.
     static const int max_n = [] { const char* e = getenv("UPMIX_FB_MAX_N"); return e ? atoi(e) : 512; }();
     if (n_fft > max_n) return;
     switch (n_fft) {
@@ -25,6 +24,7 @@ void fb_plan(int n_fft, int* ra, int* rb, int* ha) {
         default: break;
     }
 }
+int fb_frames_per_tile(int n_fft) { return n_fft == 256 ? FbCfg<256>::F : n_fft == 512 ? FbCfg<512>::F : FbCfg<1024>::F; }
 int fb_ctas_per_sm(int n_fft) { return n_fft == 256 ? FbCfg<256>::CTAS : n_fft == 512 ? FbCfg<512>::CTAS : FbCfg<1024>::CTAS; }
 
 cudaError_t launch_band_fb(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st) {

@@ -27,20 +27,37 @@
 
 namespace upmix {
 
-constexpr int FB_QS = 17;         // row stride (float2) of a 16-lane tile
+#ifndef UPMIX_FB1024_F
+#define UPMIX_FB1024_F 8          // frames per tile of the 1024-point kernel (16: one CTA of 512 threads per SM; 8: two of 256)
+#endif
 
 template <int N> struct FbCfg;
-// RA x RB = N (forward and inverse of Ls + iRs), HA x 16 = N/2 (centre); CTAS = CTAs per SM the smem / registers allow
-template <> struct FbCfg<1024> { static constexpr int RA = 32, RB = 32, HA = 32, CTAS = 1; };
-template <> struct FbCfg<512>  { static constexpr int RA = 32, RB = 16, HA = 16, CTAS = 2; };
-template <> struct FbCfg<256>  { static constexpr int RA = 16, RB = 16, HA = 8,  CTAS = 4; };
+// RA x RB = N (forward and inverse of Ls + iRs), HA x 16 = N/2 (centre); F = frames per tile (= lanes per butterfly row);
+// CTAS = CTAs per SM the smem / registers allow
+template <> struct FbCfg<1024> { static constexpr int RA = 32, RB = 32, HA = 32, F = UPMIX_FB1024_F, CTAS = F == 16 ? 1 : 2; };
+template <> struct FbCfg<512>  { static constexpr int RA = 32, RB = 16, HA = 16, F = 16, CTAS = 2; };
+template <> struct FbCfg<256>  { static constexpr int RA = 16, RB = 16, HA = 8,  F = 16, CTAS = 4; };
 
-template <int N> __host__ __device__ constexpr int fb_stage_stride() { return N / 4 + 2; }     // floats per staged hop row: 2f + m never collides
-// the 1024-point kernel (one CTA of 512 threads per SM: 128 registers) keeps the overlap-add carries of lanes 0..2 in
+// Tile layout: buf[point][frame].  Row `p` of the tile starts at fb_ro<F>(p) (in float2):
+//   F = 16: p * 17 -- a half-warp is one row, the odd stride keeps every pass conflict-free;
+//   F = 8:  (p & 31) * 8 + (p >> 5) * 264 -- a half-warp holds TWO rows (butterfly rows jb, jb + 1), 16 words each, which
+//           must fall into different halves of the 32 banks: rows one apart do (8 float2 = 16 words), rows 32 apart --
+//           the first-pass scatter j * 32 + r -- do because every block of 32 rows is followed by one row of padding
+//           (264 = 33 * 8).
+// Both are (p & 31) * S1 + (p >> 5) * S32 with S32 = 32 * S1 for F = 16.
+template <int F> struct FbLay { static constexpr int S1 = F == 16 ? 17 : 8, S32 = F == 16 ? 32 * 17 : 33 * 8; };
+template <int F> __host__ __device__ __forceinline__ constexpr int fb_ro(int p) { return (p & 31) * FbLay<F>::S1 + (p >> 5) * FbLay<F>::S32; }
+// offset of `rows` rows further down, valid when the walk does not leave / cross blocks irregularly: rows a multiple of 32,
+// or (F = 16) anything
+template <int F> __host__ __device__ constexpr int fb_step(int rows) { return F == 16 ? rows * 17 : (rows / 32) * FbLay<F>::S32 + (rows % 32) * FbLay<F>::S1; }
+
+template <int N> __host__ __device__ constexpr int fb_stage_stride() { return N / 4 + 32 / FbCfg<N>::F; }     // floats per staged hop row: (32 / F) f + m never collides
+// the 1024-point kernel (128 registers) keeps the overlap-add carries of lanes 0..2 in
 // shared memory: [N/32 butterfly rows][3 lanes][8 + 4 outputs]
 template <int N> __host__ __device__ constexpr bool fb_carry_in_smem() { return N >= 1024; }
 template <int N> __host__ __device__ constexpr int fb_smem_bytes() {
-    return (N * FB_QS + (N / 2) * FB_QS + (fb_carry_in_smem<N>() ? (N / 32) * 3 * 12 : 0)) * (int)sizeof(float2);
+    constexpr int F = FbCfg<N>::F;
+    return (fb_ro<F>(N) + fb_ro<F>(N / 2) + (fb_carry_in_smem<N>() ? (N / 32) * 3 * 12 : 0)) * (int)sizeof(float2);
 }
 
 // v[r] *= tw[k * R + r] (CONJ: its conjugate), r = 1..R-1: the twiddles of a second pass, eight at a time (16-byte
@@ -65,22 +82,25 @@ __device__ __forceinline__ void fb_apply_tw(const float2* __restrict__ tw, int k
 enum { FB_PLAIN = 0, FB_FOLD = 1, FB_MERGED = 2 };
 
 template <int N, int MODE, bool ACCUM>
-__global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const BandDev b, const SegArgs a) {
-    constexpr int T = N / 2, M = N / 2, H = N / 4, JS = N / 32;
+__global__ void __launch_bounds__(FbCfg<N>::F * N / 32, FbCfg<N>::CTAS) band_fb_kernel(const BandDev b, const SegArgs a) {
+    constexpr int F = FbCfg<N>::F, S1 = FbLay<F>::S1;
+    constexpr int T = F * N / 32, M = N / 2, H = N / 4, JS = N / 32;
     constexpr int RA = FbCfg<N>::RA, RB = FbCfg<N>::RB, HA = FbCfg<N>::HA, HB = 16;
     constexpr int NBA = N / RA, NBB = N / RB, ITA = 32 / RA, ITB = 32 / RB;     // butterflies per sequence / per thread
     constexpr int SY = RB / 4, SC = HB / 4;                                      // last-pass outputs per hop of the frame
     constexpr int HS = fb_stage_stride<N>();
-    constexpr int IN_ROWS = 19;                                                  // hops of input a tile of 16 frames covers
+    constexpr int IN_ROWS = F + 3;                                               // hops of input a tile of F frames covers
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* buf = reinterpret_cast<float2*>(smem_raw);                           // [N][FB_QS]
-    float2* cbuf = buf + N * FB_QS;                                              // [M][FB_QS] packed centre spectrum
+    float2* buf = reinterpret_cast<float2*>(smem_raw);                           // [N rows], row p at fb_ro<F>(p)
+    float2* cbuf = buf + fb_ro<F>(N);                                            // [M rows] packed centre spectrum
     float* in_l = reinterpret_cast<float*>(buf);                                 // staged input [19][HS] x 2 (inside buf)
     float* in_r = in_l + IN_ROWS * HS;
-    float* stage = in_r + IN_ROWS * HS;                                          // finished hops [3][16][HS] (inside buf)
-    static_assert((2 * IN_ROWS * HS + 3 * 16 * HS) * 4 <= N * FB_QS * 8, "staging does not fit the transform buffer");
+    float* stage = in_r + IN_ROWS * HS;                                          // finished hops [3][F][HS] (inside buf)
+    static_assert((2 * IN_ROWS * HS + 3 * F * HS) * 4 <= fb_ro<F>(N) * 8, "staging does not fit the transform buffer");
+    static_assert(F == 16 || (RA == 32 && RB == 32 && HA == 32), "the 8-frame layout is laid out for 32 x 32 points");
+    constexpr int RPS = T / (H / 2);                                             // staged / emitted hop rows a pass of the CTA covers
 
-    const int tid = threadIdx.x, q = tid & 15, jb = tid >> 4;
+    const int tid = threadIdx.x, q = tid & (F - 1), jb = tid / F;
     const int track = blockIdx.y;
     const bool fold = MODE == FB_MERGED ? a.fold != 0 : MODE == FB_FOLD;
     const long long h0 = a.hop_begin + (long long)blockIdx.x * a.hops_per_run;
@@ -102,10 +122,10 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
         if (whole) {
             const float* __restrict__ pl = gl + (s0 - a.in_begin);
             const float* __restrict__ pr = gr + (s0 - a.in_begin);
-            // T = 2H threads, H/2 eight-byte chunks per row: a thread keeps its column and walks down four rows at a time
+            // H/2 eight-byte chunks per row: a thread keeps its column and walks down RPS rows at a time
             const int col = 2 * (tid & (H / 2 - 1));
 #pragma unroll
-            for (int row = tid / (H / 2); row < IN_ROWS; row += 4) {
+            for (int row = tid / (H / 2); row < IN_ROWS; row += RPS) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(in_l + row * HS + col)), "l"(pl + row * H + col) : "memory");
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(in_r + row * HS + col)), "l"(pr + row * H + col) : "memory");
             }
@@ -125,7 +145,7 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
     // what the next tile needs from this one, per output of this thread's last-pass butterflies: lane f < 3 keeps the
     // partial sum of the older frames of hop F0 + 16 + f (see the overlap-add below)
     constexpr bool CSM = fb_carry_in_smem<N>();
-    float2* carry_sm = cbuf + M * FB_QS + (jb * 3 + (q < 3 ? q : 0)) * 12;     // (CSM) this thread's 12 carries, lanes 0..2 only
+    float2* carry_sm = cbuf + fb_ro<F>(M) + (jb * 3 + (q < 3 ? q : 0)) * 12;   // (CSM) this thread's 12 carries, lanes 0..2 only
     float2 carry_y[CSM ? 1 : ITB][CSM ? 1 : SY], carry_c[CSM ? 1 : SC];
     if constexpr (CSM) {
         static_assert(ITB * SY + SC == 12, "carry layout");
@@ -146,9 +166,9 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
     auto overlap_add = [&](float2 x0, float2 x1, float2 x2, float2 x3, float2& carry) -> float2 {
         const unsigned FULL = 0xffffffffu;
         float2 t1, t2, t3;
-        t1.x = __shfl_up_sync(FULL, x1.x, 1, 16); t1.y = __shfl_up_sync(FULL, x1.y, 1, 16);
-        t2.x = __shfl_up_sync(FULL, x2.x, 2, 16); t2.y = __shfl_up_sync(FULL, x2.y, 2, 16);
-        t3.x = __shfl_up_sync(FULL, x3.x, 3, 16); t3.y = __shfl_up_sync(FULL, x3.y, 3, 16);
+        t1.x = __shfl_up_sync(FULL, x1.x, 1, F); t1.y = __shfl_up_sync(FULL, x1.y, 1, F);
+        t2.x = __shfl_up_sync(FULL, x2.x, 2, F); t2.y = __shfl_up_sync(FULL, x2.y, 2, F);
+        t3.x = __shfl_up_sync(FULL, x3.x, 3, F); t3.y = __shfl_up_sync(FULL, x3.y, 3, F);
         // lanes 0..2: the older frames are the previous tile's (carry: lane 0 holds (y13 + y14) + y15, lane 1 y14 + y15,
         // lane 2 y15, each the matching hop segment)
         // (selects, no branches: lane 2 adds carry + t2, lane 1 keeps the carry, lane 0 adds nothing but its own frame;
@@ -157,22 +177,22 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
         const float2 A = cadd(q >= 3 ? t3 : carry, q >= 2 ? t2 : zero);
         const float2 B = cadd(A, q >= 1 ? t1 : zero);
         const float2 sum = cadd(B, x0);
-        // carry for the next tile: lane 13 (x3 + x2@14) + x1@15, lane 14 x3 + x2@15, lane 15 x3 -> lanes 0, 1, 2
+        // carry for the next tile (F = 16): lane 13 (x3 + x2@14) + x1@15, lane 14 x3 + x2@15, lane 15 x3 -> lanes 0, 1, 2
         float2 d1, d2;
-        d1.x = __shfl_down_sync(FULL, x2.x, 1, 16); d1.y = __shfl_down_sync(FULL, x2.y, 1, 16);
-        d2.x = __shfl_down_sync(FULL, x1.x, 2, 16); d2.y = __shfl_down_sync(FULL, x1.y, 2, 16);
-        const float2 A2 = cadd(x3, q <= 14 ? d1 : zero);
-        const float2 v = cadd(A2, q == 13 ? d2 : zero);
-        const int src = (q < 3 ? 13 + q : q);
-        carry.x = __shfl_sync(FULL, v.x, src, 16);
-        carry.y = __shfl_sync(FULL, v.y, src, 16);
+        d1.x = __shfl_down_sync(FULL, x2.x, 1, F); d1.y = __shfl_down_sync(FULL, x2.y, 1, F);
+        d2.x = __shfl_down_sync(FULL, x1.x, 2, F); d2.y = __shfl_down_sync(FULL, x1.y, 2, F);
+        const float2 A2 = cadd(x3, q <= F - 2 ? d1 : zero);
+        const float2 v = cadd(A2, q == F - 3 ? d2 : zero);
+        const int src = (q < 3 ? F - 3 + q : q);
+        carry.x = __shfl_sync(FULL, v.x, src, F);
+        carry.y = __shfl_sync(FULL, v.y, src, F);
         return sum;
     };
 
     long long F0 = h0 - 3;                                       // the first tile starts with the three frames before the run
     stage_input(F0);
 #pragma unroll 1
-    for (; F0 < h1; F0 += 16) {
+    for (; F0 < h1; F0 += F) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
 
@@ -196,9 +216,9 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
             for (int it = 0; it < ITA; it++) {
                 const int j = jb + it * JS;
                 Dft<RA, -1>::run(v[it]);
-                float2* __restrict__ dst = buf + (j * RA) * FB_QS + q;
+                float2* __restrict__ dst = buf + fb_ro<F>(j * RA) + q;
 #pragma unroll
-                for (int r = 0; r < RA; r++) dst[r * FB_QS] = v[it][r];
+                for (int r = 0; r < RA; r++) dst[r * S1] = v[it][r];
             }
         }
         __syncthreads();
@@ -207,9 +227,9 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
             float2 v[ITB][RB];
 #pragma unroll
             for (int it = 0; it < ITB; it++) {
-                const float2* __restrict__ src = buf + (jb + it * JS) * FB_QS + q;
+                const float2* __restrict__ src = buf + fb_ro<F>(jb + it * JS) + q;
 #pragma unroll
-                for (int r = 0; r < RB; r++) v[it][r] = src[r * NBB * FB_QS];
+                for (int r = 0; r < RB; r++) v[it][r] = src[r * fb_step<F>(NBB)];
             }
             __syncthreads();
 #pragma unroll
@@ -217,9 +237,9 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
                 const int j = jb + it * JS;
                 fb_apply_tw<RB, false>(b.fb.tw_full, j, v[it]);
                 Dft<RB, -1>::run(v[it]);
-                float2* __restrict__ dst = buf + j * FB_QS + q;
+                float2* __restrict__ dst = buf + fb_ro<F>(j) + q;
 #pragma unroll
-                for (int r = 0; r < RB; r++) dst[r * RA * FB_QS] = v[it][r];
+                for (int r = 0; r < RB; r++) dst[r * fb_step<F>(RA)] = v[it][r];
             }
         }
         __syncthreads();
@@ -228,10 +248,10 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
         {
             auto mask_item = [&](int k) {
                 const int k2 = M - k, km = (N - k) & (N - 1);
-                float2* __restrict__ p1 = buf + k * FB_QS + q;
-                float2* __restrict__ p1m = buf + km * FB_QS + q;
-                float2* __restrict__ p2 = buf + k2 * FB_QS + q;
-                float2* __restrict__ p2m = buf + (M + k) * FB_QS + q;
+                float2* __restrict__ p1 = buf + fb_ro<F>(k) + q;
+                float2* __restrict__ p1m = buf + fb_ro<F>(km) + q;
+                float2* __restrict__ p2 = buf + fb_ro<F>(k2) + q;
+                float2* __restrict__ p2m = buf + fb_ro<F>(M + k) + q;
                 const float g1 = __ldg(gain + k), g2 = __ldg(gain + k2);
                 const float2 wp = __ldg(b.tw_pack + k);
                 // (no shortcut for zero gains: this kernel serves dense bands; a zero gain gives exact zeros anyway, and
@@ -257,8 +277,8 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
                 if (!fold) {
                     float2 zk, zmk;
                     pack_pair(c1, c2, wp, zk, zmk);
-                    cbuf[k * FB_QS + q] = zk;
-                    if (k > 0) cbuf[k2 * FB_QS + q] = zmk;
+                    cbuf[fb_ro<F>(k) + q] = zk;
+                    if (k > 0) cbuf[fb_ro<F>(k2) + q] = zmk;
                 }
             };
 #pragma unroll 4
@@ -272,17 +292,17 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
             float2 v[ITA][RA];
 #pragma unroll
             for (int it = 0; it < ITA; it++) {
-                const float2* __restrict__ src = buf + (jb + it * JS) * FB_QS + q;
+                const float2* __restrict__ src = buf + fb_ro<F>(jb + it * JS) + q;
 #pragma unroll
-                for (int r = 0; r < RA; r++) v[it][r] = src[r * NBA * FB_QS];
+                for (int r = 0; r < RA; r++) v[it][r] = src[r * fb_step<F>(NBA)];
             }
             __syncthreads();
 #pragma unroll
             for (int it = 0; it < ITA; it++) {
                 Dft<RA, +1>::run(v[it]);
-                float2* __restrict__ dst = buf + ((jb + it * JS) * RA) * FB_QS + q;
+                float2* __restrict__ dst = buf + fb_ro<F>((jb + it * JS) * RA) + q;
 #pragma unroll
-                for (int r = 0; r < RA; r++) dst[r * FB_QS] = v[it][r];
+                for (int r = 0; r < RA; r++) dst[r * S1] = v[it][r];
             }
         }
         __syncthreads();
@@ -292,12 +312,12 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
             float2 v[ITB][RB];
 #pragma unroll
             for (int it = 0; it < ITB; it++) {
-                const float2* __restrict__ src = buf + (jb + it * JS) * FB_QS + q;
+                const float2* __restrict__ src = buf + fb_ro<F>(jb + it * JS) + q;
 #pragma unroll
-                for (int r = 0; r < RB; r++) v[it][r] = src[r * NBB * FB_QS];
+                for (int r = 0; r < RB; r++) v[it][r] = src[r * fb_step<F>(NBB)];
             }
             __syncthreads();                                     // buf is free: the stage and the next tile's input live in it
-            if (F0 + 16 < h1) stage_input(F0 + 16);
+            if (F0 + F < h1) stage_input(F0 + F);
 #pragma unroll
             for (int it = 0; it < ITB; it++) {
                 const int j = jb + it * JS;
@@ -316,8 +336,8 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
                         s = overlap_add(v[it][rr], v[it][SY + rr], v[it][2 * SY + rr], v[it][3 * SY + rr], carry_y[it][rr]);
                     }
                     const int m = j + rr * RA;
-                    stage[(16 + q) * HS + m] = s.x;
-                    stage[(32 + q) * HS + m] = s.y;
+                    stage[(F + q) * HS + m] = s.x;
+                    stage[(2 * F + q) * HS + m] = s.y;
                 }
             }
         }
@@ -330,9 +350,10 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
                 if (act) {
 #pragma unroll
                     for (int it = 0; it < ITH; it++) {
-                        const float2* __restrict__ src = cbuf + (jb + it * JS) * FB_QS + q;
+                        // (F = 8: NBH = 16 and jb < 16, so row jb + 16 r is row jb + 16 (r & 1) of block r >> 1)
+                        const float2* __restrict__ src = cbuf + fb_ro<F>(jb + it * JS) + q;
 #pragma unroll
-                        for (int r = 0; r < HA; r++) v[it][r] = src[r * NBH * FB_QS];
+                        for (int r = 0; r < HA; r++) v[it][r] = src[F == 16 ? r * NBH * 17 : fb_ro<F>(r * NBH)];
                     }
                 }
                 __syncthreads();
@@ -340,9 +361,9 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
 #pragma unroll
                     for (int it = 0; it < ITH; it++) {
                         Dft<HA, +1>::run(v[it]);
-                        float2* __restrict__ dst = cbuf + ((jb + it * JS) * HA) * FB_QS + q;
+                        float2* __restrict__ dst = cbuf + fb_ro<F>((jb + it * JS) * HA) + q;
 #pragma unroll
-                        for (int r = 0; r < HA; r++) dst[r * FB_QS] = v[it][r];
+                        for (int r = 0; r < HA; r++) dst[r * S1] = v[it][r];
                     }
                 }
             }
@@ -351,9 +372,9 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
                 constexpr int NBL = M / HB;                       // = HA: butterflies per sequence of the last pass
                 float2 v[HB];
                 const int j = jb;                                 // T / 16 = N / 32 = M / 16 butterflies per sequence: one each
-                const float2* __restrict__ src = cbuf + j * FB_QS + q;
+                const float2* __restrict__ src = cbuf + fb_ro<F>(j) + q;
 #pragma unroll
-                for (int r = 0; r < HB; r++) v[r] = src[r * NBL * FB_QS];
+                for (int r = 0; r < HB; r++) v[r] = src[F == 16 ? r * NBL * 17 : fb_ro<F>(r * NBL)];
                 fb_apply_tw<HB, true>(b.fb.tw_half, j, v);
                 Dft<HB, +1>::run(v);
 #pragma unroll
@@ -382,40 +403,40 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
             const long long sb = F0 * H;                          // first sample of the tile's first hop
             // samples [e_lo, e_hi) of the tile's span go out: hops of this run only (the first tile's first three hops
             // are incomplete), inside the segment
-            const long long lo = max(max(h0 * H, a.seg_begin), sb), hi = min(min(h1 * H, a.seg_end), sb + 16LL * H);
+            const long long lo = max(max(h0 * H, a.seg_begin), sb), hi = min(min(h1 * H, a.seg_end), sb + (long long)F * H);
             const int e_lo = (int)(lo - sb), e_hi = (int)(hi - sb);
             if (e_hi > e_lo) {
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
                     if (ch == 0 && fold) continue;
                     float* __restrict__ po = outp[ch] + (sb - a.out_begin);
-                    const float* __restrict__ sg = stage + ch * 16 * HS;
+                    const float* __restrict__ sg = stage + ch * F * HS;
                     const bool vec = (reinterpret_cast<uintptr_t>(po) & 7) == 0;      // CTA-uniform
-                    if (vec && e_lo == 0 && e_hi == 16 * H) {                           // the usual tile: every hop goes out whole
-                        float2 pv[(16 * H / 2) / T];
+                    if (vec && e_lo == 0 && e_hi == F * H) {                           // the usual tile: every hop goes out whole
+                        float2 pv[(F * H / 2) / T];
                         if (ACCUM) {
 #pragma unroll
-                            for (int i = 0; i < (16 * H / 2) / T; i++) pv[i] = __ldcs(reinterpret_cast<const float2*>(po) + tid + i * T);
+                            for (int i = 0; i < (F * H / 2) / T; i++) pv[i] = __ldcs(reinterpret_cast<const float2*>(po) + tid + i * T);
                         }
-                        // T = 2H threads, H/2 float2 per hop row: a thread keeps its column, four hops further each time
+                        // H/2 float2 per hop row: a thread keeps its column, RPS hops further each time
                         const float* __restrict__ sg0 = sg + (tid / (H / 2)) * HS + 2 * (tid & (H / 2 - 1));
 #pragma unroll
-                        for (int i = 0; i < (16 * H / 2) / T; i++) {
-                            float2 s = *reinterpret_cast<const float2*>(sg0 + 4 * i * HS);
+                        for (int i = 0; i < (F * H / 2) / T; i++) {
+                            float2 s = *reinterpret_cast<const float2*>(sg0 + RPS * i * HS);
                             if (ACCUM) s = make_float2(pv[i].x + s.x, pv[i].y + s.y);
                             __stcs(reinterpret_cast<float2*>(po) + tid + i * T, s);
                         }
                     } else if (vec) {
-                        float2 pv[(16 * H / 2 + T - 1) / T];
+                        float2 pv[(F * H / 2 + T - 1) / T];
                         if (ACCUM) {
 #pragma unroll
-                            for (int i = 0; i < (16 * H / 2) / T; i++) {
+                            for (int i = 0; i < (F * H / 2) / T; i++) {
                                 const int e = 2 * (tid + i * T);
                                 if (e >= e_lo && e + 1 < e_hi) pv[i] = __ldcs(reinterpret_cast<const float2*>(po + e));
                             }
                         }
 #pragma unroll
-                        for (int i = 0; i < (16 * H / 2) / T; i++) {
+                        for (int i = 0; i < (F * H / 2) / T; i++) {
                             const int e = 2 * (tid + i * T);
                             const int f = e / H, m = e - f * H;
                             float2 s = *reinterpret_cast<const float2*>(sg + f * HS + m);
@@ -428,7 +449,7 @@ __global__ void __launch_bounds__(N / 2, FbCfg<N>::CTAS) band_fb_kernel(const Ba
                             }
                         }
                     } else {
-                        for (int e = tid; e < 16 * H; e += T) {
+                        for (int e = tid; e < F * H; e += T) {
                             const int f = e / H, m = e - f * H;
                             const float s = sg[f * HS + m];
                             if (e >= e_lo && e < e_hi) po[e] = ACCUM ? po[e] + s : s;
@@ -446,10 +467,10 @@ static cudaError_t launch_fb_nm(const BandDev& b, const SegArgs& a, int n_runs, 
     cudaError_t e;
     if (a.accum) {
         if ((e = cudaFuncSetAttribute(band_fb_kernel<N, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb_smem_bytes<N>())) != cudaSuccess) return e;
-        band_fb_kernel<N, MODE, true><<<dim3(n_runs, n_tracks), N / 2, fb_smem_bytes<N>(), st>>>(b, a);
+        band_fb_kernel<N, MODE, true><<<dim3(n_runs, n_tracks), FbCfg<N>::F * N / 32, fb_smem_bytes<N>(), st>>>(b, a);
     } else {
         if ((e = cudaFuncSetAttribute(band_fb_kernel<N, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb_smem_bytes<N>())) != cudaSuccess) return e;
-        band_fb_kernel<N, MODE, false><<<dim3(n_runs, n_tracks), N / 2, fb_smem_bytes<N>(), st>>>(b, a);
+        band_fb_kernel<N, MODE, false><<<dim3(n_runs, n_tracks), FbCfg<N>::F * N / 32, fb_smem_bytes<N>(), st>>>(b, a);
     }
     return cudaGetLastError();
 }

@@ -20,6 +20,7 @@ cudaError_t launch_col_inv_frame(const BandDev& b, const WaveArgs& w, float* rin
 cudaError_t launch_band_fb(const BandDev& b, const SegArgs& a, int n_runs, int n_tracks, cudaStream_t st);
 void fb_plan(int n_fft, int* ra, int* rb, int* ha);
 int fb_ctas_per_sm(int n_fft);
+int fb_frames_per_tile(int n_fft);
 // decimated path (upmix_dec.cu): forward transform + mask of the wave's frames; inverse + overlap-add of a range of hops
 cudaError_t launch_dec_fwd(const BandDev& b, const SegArgs& a, const DecWave& w, int n_tracks, cudaStream_t st);
 cudaError_t launch_dec_inv(const BandDev& b, const SegArgs& a, const DecWave& w, int n_runs, int n_tracks, bool centre,
