@@ -73,15 +73,17 @@ sequence instead of 8192 / 65536 (N log P + O(KQ) instead of N log N) -- which i
 One frame per CTA (`band_fused_kernel<1024>`, the bench's dominant launch; `roofline.traffic` in bench.py comes from this capture):
 
 {s_fused}
-Frame-batched, 16 frames per tile (`band_fb_kernel`, upmix_fb.cuh; serves 256 and 512 points by default):
+Frame-batched (`band_fb_kernel`, upmix_fb.cuh; serves 256 and 512 points by default, 16 frames per tile; the 1024-point capture below runs 8-frame tiles):
 
 {s_fb512}
 {s_fb1024}
-The frame-batched 1024-point kernel executes 12 % fewer warp instructions than the one-frame kernel with 30 % fewer shared-memory
-wavefronts and a tenth of its bank conflicts, but a 16-frame tile needs 209 KB of shared memory: one CTA of 512 threads per SM,
-every barrier stalls the whole SM, and it issues on 36-40 % of cycles against 50 % -- 5.09 against 4.85 ms per band-hour, so 1024
-points keep the one-frame kernel (UPMIX_FB_MAX_N=1024 switches).  At 512 points (two CTAs per SM) and 256 points (four) the
-frame-batched kernel wins: 4.11 against 5.01 and 3.71 against 5.65 ms per band-hour.
+The frame-batched 1024-point kernel (8-frame tiles, two CTAs of 256 threads per SM; the 16-frame tile of one 512-thread CTA
+took 1015 us) executes 13 % fewer warp instructions than the one-frame kernel with 21 % fewer shared-memory wavefronts, but
+its tiles leave 23 KB of L1 (shared-memory carve-out 233 KB): 59 % of the sectors its table loads ask for (pass twiddles,
+windows, gains) come from L2 -- `long_scoreboard` on the multiply after the twiddle `LDG.128` leads its stalls -- where the
+one-frame kernel (88 KB of L1) hits 99 %.  4.71 against 4.60 ms per band-hour, so 1024 points keep the one-frame kernel
+(UPMIX_FB_MAX_N=1024 switches).  At 512 points (two CTAs per SM) and 256 points (four) the frame-batched kernel wins: 4.11
+against 5.01 and 3.71 against 5.65 ms per band-hour.
 """
 open(os.path.join(ROOT, "profiles", "r02_ncu_summary.md"), "w").write(md)
 hh = hashlib.sha1()
