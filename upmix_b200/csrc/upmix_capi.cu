@@ -874,6 +874,10 @@ int64_t stream_tmp_ring_bytes(const UpmixPlan* plan, int n_tracks) {
     return round_up(floats * (int64_t)sizeof(float), 256);
 }
 
+// parameter lists of stream_stage_kernel / band_sum_kernel (upmix_kernels.cu), whose graph nodes get new I/O pointers per block
+constexpr int STREAM_STAGE_NARGS = 8, STREAM_STAGE_IN_L = 2;
+constexpr int BAND_SUM_NARGS = 10, BAND_SUM_OUT_C = 5;
+
 struct StreamIo {
     const float* in_l;
     const float* in_r;
@@ -990,10 +994,10 @@ int upmix_stream_block(const UpmixPlan* plan, void* state, int64_t samples_done,
                 if (g.io[0] != in_l || g.io[1] != in_r) {
                     cudaKernelNodeParams kp;
                     CU_CHECK(cudaGraphKernelNodeGetParams(g.stage_node, &kp));
-                    void* args[8];
-                    for (int i = 0; i < 8; i++) args[i] = kp.kernelParams[i];
-                    args[2] = (void*)&in_l;
-                    args[3] = (void*)&in_r;
+                    void* args[STREAM_STAGE_NARGS];
+                    for (int i = 0; i < STREAM_STAGE_NARGS; i++) args[i] = kp.kernelParams[i];
+                    args[STREAM_STAGE_IN_L] = (void*)&in_l;
+                    args[STREAM_STAGE_IN_L + 1] = (void*)&in_r;
                     kp.kernelParams = args;
                     CU_CHECK(cudaGraphExecKernelNodeSetParams(g.exec, g.stage_node, &kp));
                     g.io[0] = in_l;
@@ -1002,11 +1006,11 @@ int upmix_stream_block(const UpmixPlan* plan, void* state, int64_t samples_done,
                 if (g.io[2] != out_c || g.io[3] != out_l || g.io[4] != out_r) {
                     cudaKernelNodeParams kp;
                     CU_CHECK(cudaGraphKernelNodeGetParams(g.sum_node, &kp));
-                    void* args[10];
-                    for (int i = 0; i < 10; i++) args[i] = kp.kernelParams[i];
-                    args[5] = (void*)&out_c;
-                    args[6] = (void*)&out_l;
-                    args[7] = (void*)&out_r;
+                    void* args[BAND_SUM_NARGS];
+                    for (int i = 0; i < BAND_SUM_NARGS; i++) args[i] = kp.kernelParams[i];
+                    args[BAND_SUM_OUT_C] = (void*)&out_c;
+                    args[BAND_SUM_OUT_C + 1] = (void*)&out_l;
+                    args[BAND_SUM_OUT_C + 2] = (void*)&out_r;
                     kp.kernelParams = args;
                     CU_CHECK(cudaGraphExecKernelNodeSetParams(g.exec, g.sum_node, &kp));
                     g.io[2] = out_c;

@@ -497,6 +497,8 @@ cudaError_t launch_col_inv_frame(const BandDev& b, const WaveArgs& w, float* rin
 // center_extraction.py:503-511 does.  mode 0: C, Ls, Rs.  mode 1 (fold-down, bela/upmix.cpp:295-303,
 // 487-490): out_l = sum_b (Ls_b + 0.5 C_b), out_r = sum_b (Rs_b + 0.5 C_b); out_c untouched.  mode 2: the
 // band kernels already folded the centre in (SegArgs::fold): out_l = sum_b slot_l, out_r = sum_b slot_r.
+// (upmix_stream_block patches parameters 5, 6, 7 -- out_c, out_l, out_r -- of this kernel's CUDA-graph node, 10 parameters
+// in all: keep the order, or change BAND_SUM_* in upmix_capi.cu with it.)
 template <int VEC>
 __global__ void __launch_bounds__(256) band_sum_kernel(const float* __restrict__ ws, int n_bands, int n_tracks,
                                                        long long seg_len, long long ws_seg,
@@ -544,6 +546,8 @@ __global__ void __launch_bounds__(256) band_sum_kernel(const float* __restrict__
 
 // Block streaming: stage = history ++ new block, history <- last D samples of stage, per channel and track (one CTA
 // each: the barrier orders the in-place shift of the history).  Replaces six cudaMemcpy2DAsync per block.
+// (upmix_stream_block patches parameters 2 and 3 -- in_l, in_r -- of this kernel's CUDA-graph node, 8 parameters in all:
+// keep the order, or change STREAM_STAGE_* in upmix_capi.cu with it.)
 __global__ void __launch_bounds__(1024) stream_stage_kernel(float* __restrict__ hist, float* __restrict__ stage,
                                                             const float* __restrict__ in_l, const float* __restrict__ in_r,
                                                             long long in_stride, int D, int n_new, int n_tracks) {
