@@ -155,6 +155,16 @@ def test_other_overlaps_vs_oracle(ce, overlap):
         b = uo.make_band(16384, 0.5, uo.blackman_harris, 100.0, 20000.0, sr, "raised_cosine", 25.0, 0.0)
         ref1 = uo.process_band_batched(b, L.astype(np.float64), R.astype(np.float64))
         assert_parity(ref1, e.process_all_blocks(L, R), peak, what="dense 16384, overlap 0.5")
+        # a time shard of the six-band plan is bit-identical to the same samples of the whole call
+        import torch
+        plan = ce.plan_for(ext)
+        dl, dr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+        whole = plan.process(dl, dr)
+        a, b = 32768 * 2, 32768 * 5 + 999
+        lo, hi = max(0, a - plan.halo), min(n, b + plan.halo)
+        seg = plan.process_segment(dl[lo:hi].contiguous(), dr[lo:hi].contiguous(), lo, n, a, b)
+        for w, sg in zip(whole, seg):
+            assert torch.equal(w[a:b], sg)
 
 
 @pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 255, 1000, 4097])
