@@ -38,8 +38,8 @@ typedef struct UpmixPlan UpmixPlan;
  * gain: per-bin real band-limit gain, n_fft/2+1 floats -- what _band_limit (CE:334-351) multiplies
  * both spectra with. */
 typedef struct UpmixBandDesc {
-    int32_t n_fft;
-    int32_t hop;
+    int32_t n_fft;       /* power of two in [64, 65536] */
+    int32_t hop;         /* even, divides n_fft; above 8192 points: n_fft/4 or n_fft/2 (75 % / 50 % overlap) */
     const float* ana;
     const float* syn;
     const float* gain;
@@ -119,7 +119,10 @@ int64_t upmix_stream_workspace_bytes(const UpmixPlan* plan, int n_new, int n_tra
 int64_t upmix_stream_delay(const UpmixPlan* plan);
 int upmix_stream_reset(const UpmixPlan* plan, void* state, int n_tracks, void* stream);
 /* samples_done: samples per track consumed by the previous calls since the last reset (the caller
- * keeps this count; the state itself is plain device memory). */
+ * keeps this count; the state itself is plain device memory).  Steady-state blocks (samples_done >= twice the
+ * largest n_fft) are replayed as CUDA graphs cached in the plan, one per block position modulo the largest
+ * n_fft; in / out pointers may change from block to block at no cost, `state` and `workspace` should stay
+ * put (a new pair means a new capture).  UPMIX_GRAPHS=0 in the environment at plan creation disables this. */
 int upmix_stream_block(const UpmixPlan* plan, void* state, int64_t samples_done, const float* in_l, const float* in_r,
                        int n_new, int n_tracks, int64_t in_stride, float* out_c, float* out_l, float* out_r,
                        int64_t out_stride, void* workspace, int64_t workspace_bytes, void* stream);
