@@ -58,11 +58,11 @@ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 // 6.24.  512 and 1024 points (16 points per thread, RL = 8) keep the separate passes: their best plans
 // end with a cheap radix-4 pass, which the fusion cannot use.
 #ifndef UPMIX_CFG_64
-#define UPMIX_CFG_64 mkplan(8, 8), mkplan(8, 8), mkplan(8, 4), 32, 16
+#define UPMIX_CFG_64 mkplan(8, 8), mkplan(8, 8), mkplan(8, 4), 32, 12
 #endif
 UPMIX_FUSED_CFG_X(64, UPMIX_CFG_64)
 #ifndef UPMIX_CFG_128
-#define UPMIX_CFG_128 mkplan(8, 4, 4), mkplan(8, 4, 4), mkplan(4, 4, 4), 32, 16
+#define UPMIX_CFG_128 mkplan(8, 4, 4), mkplan(8, 4, 4), mkplan(4, 4, 4), 32, 12
 #endif
 UPMIX_FUSED_CFG_X(128, UPMIX_CFG_128)
 #ifndef UPMIX_CFG_256
