@@ -559,6 +559,27 @@ def test_stream_graph_replay_and_split_runs_are_bit_identical(ce):
             assert torch.equal(outs[1][ch][d:], off[ch][:n - d])
 
 
+def test_stream_very_long_blocks(ce):
+    """Blocks above 65536 samples take the copy path of upmix_stream_block (2-D copies instead of the staging kernel, no
+    graph replay): same stream as the offline call, bit for bit."""
+    import torch
+    from upmix_b200 import _native
+    sr = 48000
+    bands = quiet(ce.chain_bands, [0, 1000, 6000], 0.75, ce.make_blackman_harris, sr, "raised_cosine", max_block_size=2048)
+    plan = ce.plan_for(bands, _native.OUT_LSCRS, _native.PLAN_STREAM_KERNELS)
+    m = 131072
+    n = 3 * m
+    L, R = uo.synth_stereo(n, 41)
+    A, B = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    off = plan.process(A, B)
+    st = plan.stream_open(1)
+    blocks = [st.block(A[i:i + m], B[i:i + m]) for i in range(0, n, m)]
+    d = st.delay
+    for ch in range(3):
+        got = torch.cat([b[ch] for b in blocks])
+        assert torch.equal(got[d:], off[ch][:n - d]) and not got[:d].any()
+
+
 def test_repeated_runs_are_bit_identical(ce):
     """compute-sanitizer's racecheck is closed on this pool, so races are looked for by their symptom: a kernel with a
     shared-memory race (a missing barrier between passes, a tile read before its cp.async / TMA copy landed, an overlap-add
